@@ -1,0 +1,54 @@
+"""Loader that imports the UNMODIFIED reference (python-2 code) under python 3.
+
+TEST INFRASTRUCTURE.  Only usable where /root/reference exists (the build container);
+used by ``oracle/make_golden.py`` to freeze fixtures and by ``tests/test_oracle.py`` to
+re-pin the restatement against the live reference.  Recipe: SURVEY.md appendix C.
+"""
+import os
+import pickle
+import sys
+import tempfile
+import types
+
+REFERENCE_ROOT = "/root/reference"
+
+
+class Py2Int(int):
+    """``fft_n/2`` must stay an int (mfcc.py:45,46,61 rely on python-2 division)."""
+
+    def __truediv__(self, o):
+        return Py2Int(int.__floordiv__(self, o)) if isinstance(o, int) else float(self) / o
+
+
+def available():
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "mfcc.py"))
+
+
+_cache = {}
+
+
+def load():
+    """Returns a namespace with the reference modules ``mfcc``, ``file_processing``,
+    ``sklearn_analyser`` and the python-2-int ``FFT_N``."""
+    if "ns" in _cache:
+        return _cache["ns"]
+    if not available():
+        raise RuntimeError("reference not mounted at %s" % REFERENCE_ROOT)
+    for p in (os.path.join(REFERENCE_ROOT, "dataset"),
+              os.path.join(REFERENCE_ROOT, "realtime_analysis"), REFERENCE_ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    sys.modules.setdefault("cPickle", pickle)                 # sklearn_analyser.py:1
+    sys.modules.setdefault("h5py", types.ModuleType("h5py"))  # dataset/file_index.py:1
+    cwd = os.getcwd()
+    os.chdir(tempfile.mkdtemp(prefix="vadref_"))              # sklearn_analyser.py:10 opens ./analyser.log
+    try:
+        import mfcc as ref_mfcc
+        import file_processing as ref_fp
+        import sklearn_analyser as ref_an
+    finally:
+        os.chdir(cwd)
+    ns = types.SimpleNamespace(mfcc=ref_mfcc, file_processing=ref_fp, sklearn_analyser=ref_an,
+                               FFT_N=Py2Int(512))
+    _cache["ns"] = ns
+    return ns
