@@ -1,0 +1,40 @@
+"""In-tree build of the C-ABI library (nvcc, sm_100a only).  ``python -m vad_b200.build``."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libvadb200.so")
+SOURCES = ["vadb200.cu"]
+DEPS = ["vadb200.cu", "vad_kernels.cuh", "vad_core.cuh", "vad_host_tables.h", "vad_tables.h",
+        os.path.join("..", "..", "include", "vadb200.h")]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "--expt-relaxed-constexpr", "-diag-suppress", "20091", "--shared", "-Xcompiler", "-fPIC"]
+
+
+def is_stale():
+    if not os.path.isfile(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu into vad_b200/libvadb200.so (cross-compiles without a GPU)."""
+    if not force and not is_stale():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.path.isfile(nvcc):
+        nvcc = "nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    r = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or r.returncode != 0:
+        sys.stderr.write(r.stdout)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed building libvadb200.so")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

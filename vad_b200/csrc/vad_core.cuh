@@ -1,0 +1,359 @@
+// vad_core.cuh -- per-thread arithmetic of the fused MFCC + FFN VAD path (sm_100a).
+//
+// Everything here is plain C++17 marked __host__ __device__, so the same code is
+//   * inlined into the CUDA kernels of vad_kernels.cu (the product), and
+//   * compiled by g++ into tests/emul/ (a host emulation of the kernels' thread/lane
+//     dataflow, used only by the CPU test-suite to validate index math and fp32 accuracy
+//     where no GPU is available).  It is NOT a CPU fallback: the C ABI never calls it on
+//     the host.
+//
+// Reference semantics restated here (paths relative to /root/reference):
+//   mfcc.py:59-61   get_spec_mag      |FFT512(frame ++ zeros)[0:256] / 512|^2, rectangular window
+//   mfcc.py:72-78   get_mfcc_from_spec  fbank dot, ==0 -> eps, log10, DCT-II ortho [:13], lifter
+//   realtime_analysis/sklearn_analyser.py:52-69,103-107   5-frame window features
+//   dataset/file_processing.py:51-66                     dataset-mode deltas
+//   learning/ffn_trainer.py:104-116                      Dense 39-64-32-16-3
+//
+// FFT layout (one 400-sample real frame -> 256 power bins), 16 threads per frame:
+//   z[n] = x[2n] + i x[2n+1], n < 256 (n >= 200 is zero padding); Z = FFT256(z) as 16 x 16
+//   Cooley-Tukey:  pass 1: thread t holds z[t + 16 j], DFT16 over j (inputs j >= 13 are
+//   structurally zero and pruned), times W256^(t k1); 16x16 transpose through shared memory;
+//   pass 2: thread k1 DFT16 over n2 -> Z[k1 + 16 k2].  Real-FFT split: X[k] = (E + W512^k O)/2
+//   with E = Z[k] + conj Z[256-k], O = -i (Z[k] - conj Z[256-k]); Z[256-k] lives in the
+//   partner thread (16 - k1) & 15 and arrives by warp shuffle.  Power is kept as |2X|^2;
+//   the 2^-20 = 1/(4*512^2) scale is folded into the mel weights.
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <type_traits>
+#include <utility>
+
+#include "vad_tables.h"
+
+#if defined(__CUDACC__)
+#define VADB_HD __host__ __device__ __forceinline__
+#define VADB_CONSTANT __constant__
+#else
+#define VADB_HD inline
+#define VADB_CONSTANT static
+#endif
+
+namespace vadb {
+
+constexpr int kFrame = 400;      // config.py:21 FRAME_SIZE
+constexpr int kHop = 160;        // config.py:22 FRAME_STEP
+constexpr int kFftN = 512;       // config.py:27 FFT_N
+constexpr int kBins = 256;       // fft_n / 2 (mfcc.py:61)
+constexpr int kNMel = 26;        // config.py:25
+constexpr int kNCep = 13;        // config.py:26
+constexpr int kNFeat = 39;       // 13 x (mfcc, d1, d2)
+constexpr int kH1 = 64, kH2 = 32, kH3 = 16, kNCls = 3;  // ffn_trainer.py:108-115
+
+// ---- constant-memory parameter block (uniform operands of FFMA: c[bank][imm]) -------------
+struct ConstParams {
+  float melw[448];               // 444 non-zero triangle weights x 2^-20, filter-major (kMelOff)
+  float dct[kNCep * kNMel];      // lifter[k] * dct2_ortho[k][n] * log10(2)   (input is log2 E)
+  float W1[kNFeat * kH1];        // Keras (in,out) layout: y = x.W + b
+  float b1[kH1];
+  float W2[kH1 * kH2];
+  float b2[kH2];
+  float W3[kH2 * kH3];
+  float b3[kH3];
+  float W4[kH3 * kNCls];
+  float b4[kNCls];
+  float pad_[1];
+};
+VADB_CONSTANT ConstParams c_par;
+
+struct cf2 { float x, y; };  // layout-compatible with float2 on both sides
+
+template <int B, int E, class F>
+VADB_HD void static_for(F&& f) {
+  if constexpr (B < E) {
+    f(std::integral_constant<int, B>{});
+    static_for<B + 1, E>(f);
+  }
+}
+
+// ---- radix-2 butterfly with compile-time twiddle W16^E:  o0 = a + w b,  o1 = a - w b -------
+template <int E>
+VADB_HD void bfly(float ar, float ai, float br, float bi, float& o0r, float& o0i, float& o1r,
+                  float& o1i) {
+  constexpr float C1 = 0.92387953251128674f;  // cos(pi/8)
+  constexpr float S1 = 0.38268343236508977f;  // sin(pi/8)
+  constexpr float R = 0.70710678118654752f;   // sqrt(1/2)
+  if constexpr (E == 0) {
+    o0r = ar + br; o0i = ai + bi; o1r = ar - br; o1i = ai - bi;
+  } else if constexpr (E == 4) {  // w = -i : w b = (bi, -br)
+    o0r = ar + bi; o0i = ai - br; o1r = ar - bi; o1i = ai + br;
+  } else if constexpr (E == 2) {  // w = R(1 - i) : w b = R(br + bi) + i R(bi - br)
+    const float s = br + bi, d = bi - br;
+    o0r = fmaf(R, s, ar); o0i = fmaf(R, d, ai); o1r = fmaf(-R, s, ar); o1i = fmaf(-R, d, ai);
+  } else if constexpr (E == 6) {  // w = R(-1 - i) : w b = R(bi - br) - i R(br + bi)
+    const float s = br + bi, d = bi - br;
+    o0r = fmaf(R, d, ar); o0i = fmaf(-R, s, ai); o1r = fmaf(-R, d, ar); o1i = fmaf(R, s, ai);
+  } else {  // general: 6 FMA
+    constexpr float wr = (E == 1) ? C1 : (E == 3) ? S1 : (E == 5) ? -S1 : -C1;
+    constexpr float wi = (E == 1) ? -S1 : (E == 3) ? -C1 : (E == 5) ? -C1 : -S1;
+    float xr = fmaf(wr, br, ar); xr = fmaf(-wi, bi, xr);
+    float xi = fmaf(wr, bi, ai); xi = fmaf(wi, br, xi);
+    o0r = xr; o0i = xi;
+    o1r = fmaf(2.0f, ar, -xr); o1i = fmaf(2.0f, ai, -xi);
+  }
+}
+
+// 16-point forward DFT (e^{-2 pi i nk/16}), natural order in and out, decimation in time.
+// Stage with sub-length m (G = 8/m classes): a = F_m,n[k] at n + 2Gk, b at a + G,
+// twiddle W16^(kG), results at n + Gk and n + Gk + 8.  Inputs with index >= NZ are zero.
+template <int NZ>
+VADB_HD void dft16(float (&xr)[16], float (&xi)[16]) {
+  float ar[16], ai[16];
+  static_for<0, 8>([&](auto N) {  // m = 1, G = 8
+    constexpr int n = N;
+    if constexpr (n + 8 < NZ) {
+      bfly<0>(xr[n], xi[n], xr[n + 8], xi[n + 8], ar[n], ai[n], ar[n + 8], ai[n + 8]);
+    } else {
+      ar[n] = xr[n]; ai[n] = xi[n]; ar[n + 8] = xr[n]; ai[n + 8] = xi[n];
+    }
+  });
+  static_for<0, 4>([&](auto N) {  // m = 2, G = 4
+    constexpr int n = N;
+    static_for<0, 2>([&](auto K) {
+      constexpr int k = K, ia = n + 8 * k, ib = ia + 4, o = n + 4 * k;
+      bfly<4 * k>(ar[ia], ai[ia], ar[ib], ai[ib], xr[o], xi[o], xr[o + 8], xi[o + 8]);
+    });
+  });
+  static_for<0, 2>([&](auto N) {  // m = 4, G = 2
+    constexpr int n = N;
+    static_for<0, 4>([&](auto K) {
+      constexpr int k = K, ia = n + 4 * k, ib = ia + 2, o = n + 2 * k;
+      bfly<2 * k>(xr[ia], xi[ia], xr[ib], xi[ib], ar[o], ai[o], ar[o + 8], ai[o + 8]);
+    });
+  });
+  static_for<0, 8>([&](auto K) {  // m = 8, G = 1
+    constexpr int k = K, ia = 2 * k, ib = ia + 1;
+    bfly<k>(ar[ia], ai[ia], ar[ib], ai[ib], xr[k], xi[k], xr[k + 8], xi[k + 8]);
+  });
+}
+
+// ---- pass 1: load, pruned DFT16, inter-pass twiddle -----------------------------------------
+// Packed int16 PCM: w32 points at the frame's first sample viewed as 32-bit words (sample
+// offset even); thread t takes complex samples t + 16 j (j = 12 only for t < 8: n < 200).
+VADB_HD void fft_load_pcm(const uint32_t* w32, int t, float (&xr)[16], float (&xi)[16]) {
+  static_for<0, 13>([&](auto J) {
+    constexpr int j = J;
+    uint32_t v = (j < 12 || t < 8) ? w32[t + 16 * j] : 0u;
+    xr[j] = static_cast<float>(static_cast<int16_t>(v & 0xffffu));
+    xi[j] = static_cast<float>(static_cast<int32_t>(v) >> 16);
+  });
+  xr[13] = xi[13] = xr[14] = xi[14] = xr[15] = xi[15] = 0.0f;
+}
+
+// Explicit float32 frames (the reference's per-frame API takes float frames, vad.py:37).
+VADB_HD void fft_load_f32(const float* fr, int frame_len, int t, float (&xr)[16],
+                          float (&xi)[16]) {
+  static_for<0, 16>([&](auto J) {
+    constexpr int j = J;
+    const int n = 2 * (t + 16 * j);
+    xr[j] = (n < frame_len) ? fr[n] : 0.0f;
+    xi[j] = (n + 1 < frame_len) ? fr[n + 1] : 0.0f;
+  });
+}
+
+// tw1: [k1][t] = W256^(t k1)
+template <int NZ>
+VADB_HD void fft_pass1(float (&xr)[16], float (&xi)[16], const cf2* tw1, int t) {
+  dft16<NZ>(xr, xi);
+  static_for<1, 16>([&](auto K) {
+    constexpr int k1 = K;
+    const cf2 w = tw1[k1 * 16 + t];
+    const float r = xr[k1], i = xi[k1];
+    xr[k1] = fmaf(r, w.x, -(i * w.y));
+    xi[k1] = fmaf(r, w.y, i * w.x);
+  });
+}
+
+// 16x16 transpose buffer of one frame: row n2 = t (pass-1 thread), column k1; row pitch 17
+// complex (34 words): the 16 threads' 64-bit row stores land on banks 2t, 2t+1 and the 64-bit
+// column loads on consecutive words -- both bank-conflict free.
+constexpr int kExchPitch = 17;
+constexpr int kExchFrame = 16 * kExchPitch;  // cf2 elements per frame
+
+VADB_HD void exch_store(cf2* ex, int t, const float (&xr)[16], const float (&xi)[16]) {
+  static_for<0, 16>([&](auto K) {
+    constexpr int k1 = K;
+    ex[t * kExchPitch + k1] = cf2{xr[k1], xi[k1]};
+  });
+}
+VADB_HD void exch_load(const cf2* ex, int k1, float (&xr)[16], float (&xi)[16]) {
+  static_for<0, 16>([&](auto N) {
+    constexpr int n2 = N;
+    const cf2 v = ex[n2 * kExchPitch + k1];
+    xr[n2] = v.x; xi[n2] = v.y;
+  });
+}
+
+// ---- real-FFT split of one bin pair (k, 256-k); returns |2 X[k]|^2 and |2 X[256-k]|^2 -------
+VADB_HD void split_pair(float ar, float ai, float br, float bi, float wr, float wi, float& plo,
+                        float& phi) {
+  const float er = ar + br, ei = ai - bi;    // E = a + conj(b)
+  const float qr = ai + bi, qi = br - ar;    // O = -i (a - conj(b))
+  float xr = fmaf(wr, qr, er); xr = fmaf(-wi, qi, xr);   // 2 X[k] = E + w O
+  float xi = fmaf(wr, qi, ei); xi = fmaf(wi, qr, xi);
+  const float yr = fmaf(2.0f, er, -xr), yi = fmaf(2.0f, ei, -xi);  // 2 conj X[256-k] = E - w O
+  plo = fmaf(xr, xr, xi * xi);
+  phi = fmaf(yr, yr, yi * yi);
+}
+
+// After pass 2 thread k1 holds Z[k1 + 16 k2] in (xr[k2], xi[k2]).  It finishes the 8 pairs
+// (k, 256-k), k = k1 + 16 k2, k2 < 8; the mirror element is Z[(16-k1) + 16 (15-k2)] on the
+// partner thread.  Thread 0 pairs with itself at index 16 - k2, so it rotates its send
+// registers by one; it also owns the self-paired bin 128 (|X|^2 = |Z|^2).
+// XCH(mine, j, is_imag, partner) returns the partner's send register j.
+// store(bin, value) receives raw power |2X|^2 for bins 0..255.
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
+template <class XCH, class STORE>
+VADB_HD void fft_split_store(const float (&xr)[16], const float (&xi)[16], int k1, const cf2* tw2,
+                             XCH&& xch, STORE&& store) {
+  float sr[16], si[16];
+  static_for<8, 16>([&](auto J) {
+    constexpr int j = J;
+    sr[j] = (k1 == 0) ? xr[(j + 1) & 15] : xr[j];
+    si[j] = (k1 == 0) ? xi[(j + 1) & 15] : xi[j];
+  });
+  const int partner = (16 - k1) & 15;
+  static_for<0, 8>([&](auto K) {
+    constexpr int k2 = K;
+    const float br = xch(sr[15 - k2], 15 - k2, false, partner);
+    const float bi = xch(si[15 - k2], 15 - k2, true, partner);
+    const cf2 w = tw2[k2 * 16 + k1];  // W512^(k1 + 16 k2)
+    float plo, phi;
+    split_pair(xr[k2], xi[k2], br, bi, w.x, w.y, plo, phi);
+    const int lo = k1 + 16 * k2;
+    store(lo, plo);
+    if (k2 != 0 || k1 != 0) store(256 - lo, phi);
+  });
+  if (k1 == 0) store(128, 4.0f * fmaf(xr[8], xr[8], xi[8] * xi[8]));
+}
+
+// ---- mel + log: lane = frame; P points at column `lane` of the [256][pitch] power tile -------
+VADB_HD float log2_energy(float e) {
+  // mfcc.py:74: exact zeros -> float64 eps = 2^-52 (exactly representable in fp32)
+  e = (e == 0.0f) ? 2.220446049250313e-16f : e;
+  return log2f(e);
+}
+
+template <int G, int PITCH, int OPITCH>
+VADB_HD void mel_group(const float* P, float* logE) {
+  static_for<0, kMelGroupCount[G]>([&](auto J) {
+    constexpr int m = kMelGroupFilter[G][J];
+    constexpr int lo = kMelLo[m], hi = kMelHi[m], off = kMelOff[m];
+    float e = 0.0f;
+    static_for<lo, hi>([&](auto K) {
+      constexpr int k = K;
+      e = fmaf(P[k * PITCH], c_par.melw[off + k - lo], e);
+    });
+    logE[m * OPITCH] = log2_energy(e);
+  });
+}
+
+template <int PITCH, int OPITCH>
+VADB_HD void mel_group_dispatch(int g, const float* P, float* logE) {
+  switch (g) {
+    case 0: mel_group<0, PITCH, OPITCH>(P, logE); break;
+    case 1: mel_group<1, PITCH, OPITCH>(P, logE); break;
+    case 2: mel_group<2, PITCH, OPITCH>(P, logE); break;
+    case 3: mel_group<3, PITCH, OPITCH>(P, logE); break;
+    case 4: mel_group<4, PITCH, OPITCH>(P, logE); break;
+    case 5: mel_group<5, PITCH, OPITCH>(P, logE); break;
+    case 6: mel_group<6, PITCH, OPITCH>(P, logE); break;
+    default: mel_group<7, PITCH, OPITCH>(P, logE); break;
+  }
+}
+
+// DCT-II(ortho)[:13] x lifter x log10(2) of the 26 log2-energies of one frame (column).
+template <int PITCH>
+VADB_HD float dct_coef(const float* logE, int c) {
+  float acc = 0.0f;
+#pragma unroll
+  for (int n = 0; n < kNMel; ++n) acc = fmaf(logE[n * PITCH], c_par.dct[c * kNMel + n], acc);
+  return acc;
+}
+
+// ---- 5-frame window features ------------------------------------------------------------------
+// r[d][k] = MFCC k of frame t-2+d.  mode 0: analyser (sklearn_analyser.py:52-69,103-107);
+// mode 1: dataset (file_processing.py:51-66).  Returns false when a feature is non-finite
+// (sigma5 == 0: the reference yields nan -> numpy argmax 0 -> non-speech).
+VADB_HD bool window_features(const float (&r)[5][kNCep], int mode, float (&x)[kNFeat]) {
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < kNCep; ++k) {
+    const float c0 = r[0][k], c1 = r[1][k], c2 = r[2][k], c3 = r[3][k], c4 = r[4][k];
+    float z = c2;
+    if (mode == 0) {
+      const float mu = ((((c0 + c1) + c2) + c3) + c4) * 0.2f;
+      const float d0 = c0 - mu, d1 = c1 - mu, d2 = c2 - mu, d3 = c3 - mu, d4 = c4 - mu;
+      const float var = fmaf(d4, d4, fmaf(d3, d3, fmaf(d2, d2, fmaf(d1, d1, d0 * d0)))) * 0.2f;
+      // exact-arithmetic semantics of np.std == 0: all five equal -> 0/0 = nan
+      const bool alleq = (c0 == c1) && (c1 == c2) && (c2 == c3) && (c3 == c4);
+      z = alleq ? NAN : d2 / sqrtf(var);
+      ok = ok && (fabsf(z) <= 3.0e38f);  // false for nan and inf
+    }
+    x[k] = z;
+    x[kNCep + k] = c3 - c1;
+    x[2 * kNCep + k] = (c4 - z) - (z - c0);
+  }
+  return ok;
+}
+
+// ---- FFN forward, one frame per thread, weights as uniform constant operands -------------------
+VADB_HD void ffn_forward(const float (&x)[kNFeat], float (&logit)[kNCls]) {
+  float h2[kH2];
+#pragma unroll
+  for (int o = 0; o < kH2; ++o) h2[o] = c_par.b2[o];
+#pragma unroll
+  for (int c = 0; c < kH1 / 8; ++c) {  // 8 layer-1 neurons at a time, streamed into layer 2
+    float h1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h1[j] = c_par.b1[8 * c + j];
+#pragma unroll
+    for (int i = 0; i < kNFeat; ++i) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h1[j] = fmaf(x[i], c_par.W1[i * kH1 + 8 * c + j], h1[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float a = fmaxf(h1[j], 0.0f);  // the duplicate ReLU (ffn_trainer.py:110) is idempotent
+#pragma unroll
+      for (int o = 0; o < kH2; ++o) h2[o] = fmaf(a, c_par.W2[(8 * c + j) * kH2 + o], h2[o]);
+    }
+  }
+  float h3[kH3];
+#pragma unroll
+  for (int o = 0; o < kH3; ++o) h3[o] = c_par.b3[o];
+#pragma unroll
+  for (int i = 0; i < kH2; ++i) {
+    const float a = fmaxf(h2[i], 0.0f);
+#pragma unroll
+    for (int o = 0; o < kH3; ++o) h3[o] = fmaf(a, c_par.W3[i * kH3 + o], h3[o]);
+  }
+#pragma unroll
+  for (int o = 0; o < kNCls; ++o) logit[o] = c_par.b4[o];
+#pragma unroll
+  for (int i = 0; i < kH3; ++i) {
+    const float a = fmaxf(h3[i], 0.0f);
+#pragma unroll
+    for (int o = 0; o < kNCls; ++o) logit[o] = fmaf(a, c_par.W4[i * kNCls + o], logit[o]);
+  }
+}
+
+// speech <=> argmax == VOICED(1) (sklearn_analyser.py:76, config.py:45-47); numpy argmax
+// takes the first maximum, so class 1 must be strictly greater than class 0 and >= class 2.
+VADB_HD uint8_t decide(const float (&logit)[kNCls]) {
+  return (logit[1] > logit[0] && logit[1] >= logit[2]) ? 1 : 0;
+}
+
+}  // namespace vadb
