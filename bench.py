@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- audio-seconds/second of the fused MFCC+FFN VAD hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (configs[2]): 1,000 h of synthetic 16 kHz int16 audio PER GPU as 360,000 x 10 s
+utterances, generated on the device (counter-based integer generator, bit-identical to
+vad_b200/synth.py) and resident in HBM (115.2 GB >> 126 MB L2) when the timed region starts.
+One step = one pass of the fused kernel over the rank's whole shard -> one uint8 label per
+output frame.  Utterances are independent, so ranks share nothing: weak scaling, no collective
+on the data path (only the timing all-reduce).
+
+Rank 0 prints ONE JSON line: value (device-resident, CUDA events, max over ranks), e2e (same
+metric through the C ABI's host-buffer entry point vadb200_vad_host: pinned host PCM -> H2D ->
+kernel -> D2H labels, every step), roofline (algorithmic FP32 flop / kernel time against a live
+FMA microbenchmark; HBM fraction alongside), cpu_baseline (the reference-shaped CPU port on the
+host cores, bounded sample), clocks and launch count.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "audio_seconds_per_second"
+UNIT = "audio-s/s"
+FLOP_PER_FRAME_FUSED = 24663   # FFT 11520 + power 768 + mel 888 + log 26 + DCT 676 + window 340 + FFN 10208 + 237
+BYTES_PER_FRAME_FUSED = 321    # 160 int16 in + 1 label out
+FP32_NOMINAL_TFLOPS = 74.4     # 148 SM x 128 lanes x 2 x 1.965 GHz (fallback denominator)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--hours-per-gpu", type=float, default=1000.0)
+    ap.add_argument("--utt-seconds", type=float, default=10.0)
+    ap.add_argument("--e2e-window-utts", type=int, default=6000, help="utterances per pinned host window (1.92 GB)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-utts-per-core", type=int, default=16)
+    ap.add_argument("--seed", type=int, default=1234)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, mx, pw, reasons = [], [], [], set()
+        for t, line in self.rows:
+            if t < t0 or t > t1 + 0.05:
+                continue
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1])); pw.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------- CPU arm
+def run_cpu_port(utts, procs, steps, warmup, utt_seconds, seed):
+    cmd = [sys.executable, "-m", "oracle.cpu_bench", "--utts", str(utts), "--procs", str(procs), "--steps", str(steps),
+           "--warmup", str(warmup), "--utt-seconds", str(utt_seconds), "--seed", str(seed)]
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    out = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=1500)
+    if out.returncode != 0:
+        raise RuntimeError("cpu_bench failed: " + out.stderr[-400:])
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def reference_arm(a):
+    """The reference's own CPU implementation of the path.  /root/reference is pure Python 2 and
+    cannot travel to the GPU box, so the line-for-line port oracle/ref_loop.py stands in
+    (cpu_baseline.kind = "port"), on all host cores with the reference's Pool.map shape."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    utts = a.cpu_utts_per_core * cores
+    r = run_cpu_port(utts, cores, a.steps, a.warmup, a.utt_seconds, a.seed)
+    sample = "%d x %.0f s synthetic utterances per step (%.0f audio-s), Pool(%d)" % (utts, a.utt_seconds,
+                                                                                     utts * a.utt_seconds, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["audio_s_per_s"], "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(a, a.gpus, sample_note="bounded sample per step: " + sample),
+        "cpu_baseline": {"value": r["audio_s_per_s"], "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": r["audio_s_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(a, n, sample_note=None):
+    c = {"workload": "cfg3: fused MFCC+FFN VAD (39-64-32-16-3, seeded Glorot weights) over %.0f h of synthetic 16 kHz "
+                     "int16 audio per GPU, %.0f s utterances, batch-sharded" % (a.hours_per_gpu, a.utt_seconds),
+         "hours_per_gpu": a.hours_per_gpu, "total_hours": a.hours_per_gpu * n, "utt_seconds": a.utt_seconds,
+         "frame": 400, "hop": 160, "n_fft": 512, "n_mel": 26, "n_ceps": 13, "parallelism": "dp%d (no collective)" % n,
+         "l2": "inputs larger than L2 (no flush needed)"}
+    if sample_note:
+        c["note"] = sample_note
+    return c
+
+
+# ----------------------------------------------------------------------------------------- GPU arm
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        reference_arm(a)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs CUDA devices (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from vad_b200 import batch, runtime
+
+    h = runtime.Handle(local, ffn_weights=runtime.glorot_ffn(0))
+    L = int(round(a.utt_seconds * 16000))
+    n_utt = int(round(a.hours_per_gpu * 3600.0 / a.utt_seconds))
+    offsets, lengths, stride = batch.uniform_layout(n_utt, L)
+    need = n_utt * stride * 2 + n_utt * 1000 + (3 << 30)
+    free, _ = torch.cuda.mem_get_info(dev)
+    if need > free:  # never drive the box out of memory: shrink and say so
+        n_utt = int((free - (4 << 30)) // (stride * 2 + 1000))
+        offsets, lengths, stride = batch.uniform_layout(n_utt, L)
+        a.hours_per_gpu = n_utt * a.utt_seconds / 3600.0
+    pcm = torch.empty(n_utt * stride + 8, dtype=torch.int16, device=dev)
+    pcm[-8:].zero_()
+    h.synth_pcm(n_utt, L, seed=a.seed, first_utt=rank * n_utt, utt_stride=stride, out=pcm)
+    plan = runtime.Plan(h, offsets, lengths, runtime.MODE_VAD)
+    labels = torch.empty(plan.total_rows, dtype=torch.uint8, device=dev)
+    audio_s = n_utt * a.utt_seconds
+    frames = plan.total_rows
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident timing ---------------------------------------------------------------------
+    for _ in range(max(a.warmup, 3)):
+        plan.vad(pcm, labels=labels)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = h.lib.vadb200_launch_count()
+    t_w0 = time.perf_counter()
+    e0.record()
+    for _ in range(a.steps):
+        plan.vad(pcm, labels=labels)
+    e1.record()
+    torch.cuda.synchronize()
+    t_w1 = time.perf_counter()
+    barrier()
+    launches = h.lib.vadb200_launch_count() - launches0
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    if sampler:
+        time.sleep(0.1)
+        sampler.stop()
+    ms_per_step = ms_total / a.steps
+    total_audio = sum_over_ranks(audio_s)
+    value = total_audio / (ms_per_step * 1e-3)
+    speech_frac = float(labels[: min(frames, 50_000_000)].float().mean().item())
+
+    # ---- end to end through the host-buffer C-ABI entry point ---------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        win = min(a.e2e_window_utts, n_utt)
+        while n_utt % win:
+            win -= 1
+        n_win = n_utt // win
+        w_off, w_len, _ = batch.uniform_layout(win, L)
+        wplan = runtime.Plan(h, w_off, w_len, runtime.MODE_VAD)
+        h_pcm = torch.empty(win * stride + 8, dtype=torch.int16).pin_memory()
+        h_pcm.copy_(pcm[: win * stride + 8])
+        h_lab = torch.empty(wplan.total_rows, dtype=torch.uint8).pin_memory()
+        torch.cuda.synchronize()
+        wplan.vad_host(h_pcm, labels_host=h_lab)                       # warm-up + sanity: same labels as the device path
+        same = bool(torch.equal(h_lab, labels[: wplan.total_rows].cpu()))
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(a.e2e_steps):
+            for _w in range(n_win):
+                wplan.vad_host(h_pcm, labels_host=h_lab)
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        e2e = {"value": total_audio * a.e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(sum_over_ranks(n_win * win * stride * 2)),
+               "d2h_bytes_per_step": int(sum_over_ranks(n_win * wplan.total_rows)),
+               "ms_per_step": 1e3 * dt / a.e2e_steps, "timing": "host wall clock around blocking C-ABI calls, max over ranks",
+               "host_window_bytes": int(win * stride * 2), "windows_per_step": n_win, "labels_match_device_path": same}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant (only) kernel -----------------------------------------------------
+    peak_reg = h.fp32_peak(0, 2048)
+    peak_const = h.fp32_peak(1, 2048)
+    peak = max(peak_reg, peak_const)
+    peak_src = "live FFMA microbenchmark on this GPU (vadb200_fp32_peak: reg %.1f / const-operand %.1f TFLOP/s); " \
+               "MEASURED_PEAKS.json has no FP32 figure" % (peak_reg, peak_const)
+    if not peak or peak <= 0:
+        peak, peak_src = FP32_NOMINAL_TFLOPS, "nominal fallback 148x128x2x1.965 GHz"
+    hbm_peak = None
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm_peak = float(json.load(f)["hbm_gbs"])
+    except Exception:
+        hbm_peak = 6650.0
+    kern_s = ms_per_step * 1e-3                     # one fused_kernel<VAD> launch per step
+    achieved = frames * FLOP_PER_FRAME_FUSED / kern_s / 1e12
+    hbm_ach = frames * BYTES_PER_FRAME_FUSED / kern_s / 1e9
+    roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "fused_kernel<2> (MFCC+FFN VAD)", "launches_per_step": 1,
+                "algorithmic_flop_per_frame": FLOP_PER_FRAME_FUSED, "frames_per_launch": int(frames),
+                "peak_source": peak_src, "nominal_fp32_tflops": FP32_NOMINAL_TFLOPS,
+                "frac_of_nominal": achieved / FP32_NOMINAL_TFLOPS,
+                "hbm": {"achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                        "algorithmic_bytes_per_frame": BYTES_PER_FRAME_FUSED}}
+
+    # ---- CPU baseline next to it (N = 1 only) ---------------------------------------------------------
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        utts = a.cpu_utts_per_core * cores
+        try:
+            r = run_cpu_port(utts, cores, 1, 1, a.utt_seconds, a.seed)
+            cpu = {"value": r["audio_s_per_s"], "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "%d x %.0f s utterances of the same synthetic workload (%.0f audio-s), "
+                             "oracle/ref_loop.py under multiprocessing.Pool(%d)" % (utts, a.utt_seconds,
+                                                                                     utts * a.utt_seconds, cores)}
+        except Exception as ex:  # the GPU numbers stand on their own
+            cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": "failed: %s" % ex}
+
+    clocks = sampler.summary(t_w0, t_w1) if sampler else None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic (device-generated counter-based int16 noise with a speech-like on/off envelope; "
+                "random-init FFN weights)",
+        "config": workload_config(a, world), "e2e": e2e, "gpu_launches": int(sum_over_ranks(launches)) if world == 1 else int(launches * world),
+        "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "frames_per_step": int(frames * world), "speech_fraction": speech_frac,
+        "gpu": torch.cuda.get_device_name(local),
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -434,8 +434,8 @@ __global__ void __launch_bounds__(kThreads) stream_feed_kernel(const BankParams 
   s_tw1[tid] = p.tw1[tid];
   if (tid < 128) s_tw2[tid] = p.tw2[tid];
   // stage frames: [hist 320 | chunk 80] per stream, then roll the history in global memory
-  for (int j = tid; j < kStepFrames * 240; j += kThreads) {  // 32-bit words: 160 hist + 80 chunk per stream
-    const int fi = j / 240, w = j - fi * 240;
+  for (int j = tid; j < kStepFrames * 200; j += kThreads) {  // 32-bit words: 160 hist + 40 chunk per stream
+    const int fi = j / 200, w = j - fi * 200;
     const int st = min(s0 + fi, p.n_streams - 1);
     const uint32_t v = (w < 160) ? reinterpret_cast<const uint32_t*>(p.hist + static_cast<long long>(st) * 320)[w]
                                  : reinterpret_cast<const uint32_t*>(p.chunks + static_cast<long long>(st) * 160)[w - 160];

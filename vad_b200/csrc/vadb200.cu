@@ -91,11 +91,16 @@ struct vadb200_bank {
 namespace {
 
 // Upload the handle's constant block if another handle (or an older version) owns the bank.
-int ensure_constants(vadb200_handle* h, cudaStream_t st) {
+// Ownership changes are rare (new handle / new weights), so they are made fully synchronous:
+// drain every stream that may still read the old constants, then copy with the blocking call,
+// so launches on ANY stream afterwards see the new block.
+int ensure_constants(vadb200_handle* h, cudaStream_t) {
   std::lock_guard<std::mutex> lk(g_const_mu);
   const unsigned long long tag = (h->id << 20) | h->version;
   if (h->device < 64 && g_const_owner[h->device] == tag) return 0;
-  CU(cudaMemcpyToSymbolAsync(c_par, &h->par, sizeof(ConstParams), 0, cudaMemcpyHostToDevice, st));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpyToSymbol(c_par, &h->par, sizeof(ConstParams), 0, cudaMemcpyHostToDevice));
+  CU(cudaDeviceSynchronize());
   if (h->device < 64) g_const_owner[h->device] = tag;
   return 0;
 }
@@ -583,7 +588,10 @@ int vadb200_stream_bank_create(vadb200_handle* h, int n_streams, vadb200_bank** 
     return cuda_fail(e, "vadb200_stream_bank_create");
   }
   *out = b;
-  return vadb200_stream_bank_reset(b, nullptr);
+  int rc = vadb200_stream_bank_reset(b, nullptr);
+  if (rc) return rc;
+  CU(cudaDeviceSynchronize());  // state is zero before any stream can feed
+  return 0;
 }
 
 int vadb200_stream_bank_destroy(vadb200_bank* b) {
