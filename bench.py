@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-utts-per-core", type=int, default=16)
+    ap.add_argument("--ffn-impl", default="tc", choices=["tc", "fp32"],
+                    help="FFN contraction: tcgen05 tensor cores (tf32 x3) or FP32 CUDA cores")
     ap.add_argument("--seed", type=int, default=1234)
     return ap.parse_args()
 
@@ -179,6 +181,7 @@ def main():
     from vad_b200 import batch, runtime
 
     h = runtime.Handle(local, ffn_weights=runtime.glorot_ffn(0))
+    h.set_ffn_impl(a.ffn_impl)
     L = int(round(a.utt_seconds * 16000))
     n_utt = int(round(a.hours_per_gpu * 3600.0 / a.utt_seconds))
     offsets, lengths, stride = batch.uniform_layout(n_utt, L)
@@ -298,7 +301,8 @@ def main():
     achieved = frames * FLOP_PER_FRAME_FUSED / kern_s / 1e12
     hbm_ach = frames * BYTES_PER_FRAME_FUSED / kern_s / 1e9
     roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "fused_kernel<2> (MFCC+FFN VAD)", "launches_per_step": 1,
+                "traffic": None, "kernel": "fused_kernel<2,%d> (MFCC+FFN VAD, FFN on %s)" % (
+                    1 if a.ffn_impl == "tc" else 0, "tcgen05 tf32x3" if a.ffn_impl == "tc" else "FP32 CUDA cores"), "launches_per_step": 1,
                 "algorithmic_flop_per_frame": FLOP_PER_FRAME_FUSED, "frames_per_launch": int(frames),
                 "peak_source": peak_src, "nominal_fp32_tflops": FP32_NOMINAL_TFLOPS,
                 "frac_of_nominal": achieved / FP32_NOMINAL_TFLOPS,
@@ -327,7 +331,7 @@ def main():
                 "random-init FFN weights)",
         "config": workload_config(a, world), "e2e": e2e, "gpu_launches": int(sum_over_ranks(launches)) if world == 1 else int(launches * world),
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-        "frames_per_step": int(frames * world), "speech_fraction": speech_frac,
+        "frames_per_step": int(frames * world), "speech_fraction": speech_frac, "ffn_impl": a.ffn_impl,
         "gpu": torch.cuda.get_device_name(local),
     }
     print(json.dumps(line))

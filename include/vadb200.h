@@ -80,6 +80,12 @@ int vadb200_set_ffn_weights(vadb200_handle* h, const float* W1, const float* b1,
                             const float* b2, const float* W3, const float* b3, const float* W4,
                             const float* b4);
 
+/* Where the FFN contraction runs: 0 = FP32 CUDA cores (constant-bank FFMA), 1 = tcgen05 tensor cores
+ * (kind::tf32, operands split hi/lo into three MMAs, fp32 accumulation in TMEM).  Both meet the
+ * logit tolerance; applies to vadb200_vad_packed / vadb200_vad_host / vadb200_ffn_predict. */
+int vadb200_set_ffn_impl(vadb200_handle* h, int impl);
+int vadb200_get_ffn_impl(vadb200_handle* h);
+
 /* ---- ragged packed batches (replaces dataset_creator.process_files' Pool.map over files,
  * dataset_creator.py:53-65, and split_into_frames, file_processing.py:80-103) ---------------
  * Utterance u occupies samples [offsets[u], offsets[u] + lengths[u]) of one int16 buffer;

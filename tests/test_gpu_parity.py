@@ -215,6 +215,82 @@ def test_host_pipeline_equals_device_path(env):
     assert torch.equal(torch.nan_to_num(logits_host), torch.nan_to_num(dev_logits.cpu()))
 
 
+# ---- tensor-core FFN (tcgen05, tf32 x3) ----------------------------------------------------------
+@pytest.fixture()
+def tc(env):
+    h, w = env
+    h.set_ffn_impl("tc")
+    yield h, w
+    h.set_ffn_impl("fp32")
+
+
+def test_tc_ffn_rows_vs_oracle(tc):
+    h, w = tc
+    assert h.ffn_impl == 1
+    rng = np.random.default_rng(5)
+    for n in (1, 127, 128, 129, 1000):
+        x = (rng.standard_normal((n, 39)) * np.array([1.0] * 13 + [3.0] * 13 + [30.0] * 13)).astype(np.float32)
+        x[0, :] = 0.0
+        if n > 5:
+            x[5, 7] = np.nan
+        labels, logits = h.ffn_predict(x)
+        labels, logits = labels.cpu().numpy(), logits.cpu().numpy()
+        ref_logits, _ = rm.ffn_forward(x, w)
+        fin = np.isfinite(x).all(axis=1)
+        assert np.array_equal(np.isfinite(logits).all(axis=1), fin) and np.all(labels[~fin] == 0)
+        err = np.abs(logits[fin] - ref_logits[fin])
+        assert np.all(err <= LOGIT_ATOL + LOGIT_RTOL * np.abs(ref_logits[fin])), err.max()
+        srt = np.sort(ref_logits[fin], axis=1)
+        dec = (srt[:, -1] - srt[:, -2]) > 2 * (LOGIT_ATOL + LOGIT_RTOL * np.abs(srt[:, -1]))
+        assert np.array_equal(labels[fin][dec], rm.decide(ref_logits)[fin][dec])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_tc_fused_golden_utterances(tc, utts, name):
+    from vad_b200 import batch
+    h, w = tc
+    pcm = utts[name + "/pcm"]
+    labels, logits = batch.vad_batch([pcm], handle=h, want_logits=True)
+    check_vad(labels[0].cpu().numpy(), logits[0].cpu().numpy(), pcm, w)
+
+
+def test_tc_fused_ragged_and_60s(tc):
+    from vad_b200 import batch
+    h, w = tc
+    lens = [0, 401, 1041, 1201, 16000, 32003, 48017, 561, 25000, 160000]
+    utts = [synth_utterance(7, i, n) for i, n in enumerate(lens)]
+    labels, logits = batch.vad_batch(utts, handle=h, want_logits=True)
+    for u, la, lo in zip(utts, labels, logits):
+        check_vad(la.cpu().numpy(), lo.cpu().numpy(), u, w)
+    pcm = synth_utterance(1234, 0, 960000)
+    pcm[200000:216000] = 0
+    labels, logits = batch.vad_batch([pcm], handle=h, want_logits=True)
+    check_vad(labels[0].cpu().numpy(), logits[0].cpu().numpy(), pcm, w)
+
+
+def test_tc_and_fp32_paths_agree_on_batch(env):
+    import torch
+    from vad_b200 import batch, runtime
+    h, w = env
+    n_utt, L = 128, 160000
+    off, ln, stride = batch.uniform_layout(n_utt, L)
+    pcm = h.synth_pcm(n_utt, L, seed=99, first_utt=0, utt_stride=stride)
+    plan = runtime.Plan(h, off, ln, runtime.MODE_VAD)
+    la0, lo0, _ = plan.vad(pcm, want_logits=True)
+    h.set_ffn_impl("tc")
+    try:
+        la1, lo1, _ = plan.vad(pcm, want_logits=True)
+        la2, _, _ = plan.vad(pcm)
+    finally:
+        h.set_ffn_impl("fp32")
+    assert torch.equal(la1, la2)
+    d = (lo0 - lo1).abs()
+    fin = torch.isfinite(lo0).all(dim=1)
+    assert torch.equal(torch.isfinite(lo1).all(dim=1), fin)
+    assert float(d[fin].max()) < 5e-4
+    assert float((la0 != la1).float().mean()) < 1e-3
+
+
 # ---- analyser / streaming ------------------------------------------------------------------------
 def test_fused_analyser_feed_frame_contract(env):
     from vad_b200.analyser import FusedAnalyser, FFNClassifier

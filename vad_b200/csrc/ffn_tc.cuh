@@ -1,0 +1,281 @@
+// ffn_tc.cuh -- Dense 39-64-32-16-3 (learning/ffn_trainer.py:104-116) on the 5th-gen tensor
+// cores: tcgen05.mma kind::tf32, accumulators and activations in TMEM.
+//
+// Why tensor cores here (ncu, profiles/README.md r1a/r1b): with FP32 FFMAs the FFN block phase
+// took 47 % of the fused kernel at 32 % FMA-pipe utilisation -- bound by delivering 5,104 weight
+// operands per frame (LDCU) and by instruction fetch, not by math.  As an M=128-frame GEMM chain
+// the same contraction is ~1 k CUDA-core instructions per frame (feature build + epilogues).
+//
+// Precision: logits must stay within 1e-3 of the float64 oracle, so every operand is split into
+// two tf32 terms, x = x_hi + x_lo (x_hi = top 19 bits, x_lo = x - x_hi exactly), and each layer
+// issues three MMAs per k-step: a_hi.b_hi + a_lo.b_hi + a_hi.b_lo (the dropped lo.lo term is
+// <= 2^-20 relative).  Accumulation is fp32 in TMEM.
+//
+// One tile = 128 frames = 128 threads (4 warps; warp w owns TMEM lanes 32 (w % 4) ..+31, thread =
+// frame = lane).  TMEM map (256 columns per CTA, 2 CTAs per SM = all 512):
+//   [  0,128)  A operand of the current layer: hi in [0,K), lo in [K,2K)   (K = 40, 64, 32, 16)
+//   [128,192)  D1 (64)  -> later D3 [128,144) and D4 [144,160)
+//   [192,224)  D2 (32)
+// Weights (B operand, N x K, K-major, SWIZZLE_NONE canonical layout: 8x16B core matrices,
+// core (kc, nc) at (kc * N/8 + nc) * 128 B, so SBO = 128 B and LBO = N/8 * 128 B) are prepared
+// once on the host (hi block then lo block per layer) and arrive in shared memory by one TMA
+// bulk copy.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "vad_core.cuh"
+
+namespace vadb {
+
+constexpr int kTcK1 = 40, kTcN1 = 64;   // 39 -> 40 (k multiple of 8), 64
+constexpr int kTcK2 = 64, kTcN2 = 32;
+constexpr int kTcK3 = 32, kTcN3 = 16;
+constexpr int kTcK4 = 16, kTcN4 = 16;   // 3 -> 16 (M = 128 needs N % 16 == 0)
+constexpr int kTcBlk1 = kTcK1 * kTcN1 * 4, kTcBlk2 = kTcK2 * kTcN2 * 4, kTcBlk3 = kTcK3 * kTcN3 * 4,
+              kTcBlk4 = kTcK4 * kTcN4 * 4;
+constexpr int kTcOff1 = 0;
+constexpr int kTcOff2 = kTcOff1 + 2 * kTcBlk1;
+constexpr int kTcOff3 = kTcOff2 + 2 * kTcBlk2;
+constexpr int kTcOff4 = kTcOff3 + 2 * kTcBlk3;
+constexpr int kTcBlobBytes = kTcOff4 + 2 * kTcBlk4;  // 43,008
+constexpr int kTmemCols = 256;
+constexpr int kTmA = 0, kTmD1 = 128, kTmD3 = 128, kTmD4 = 144, kTmD2 = 192;
+
+// ---- host side: pack Keras (in,out) weights into the canonical hi/lo blob --------------------------
+inline float tf32_hi(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u &= 0xFFFFE000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+inline void tc_pack_layer(const float* W /*[k_real][n_real]*/, int k_real, int n_real, int K, int N, float* hi,
+                          float* lo) {
+  for (int i = 0; i < K * N; ++i) hi[i] = lo[i] = 0.0f;
+  for (int n = 0; n < n_real; ++n)
+    for (int k = 0; k < k_real; ++k) {
+      const float w = W[k * n_real + n];
+      const int idx = ((k / 4) * (N / 8) + (n / 8)) * 32 + (n % 8) * 4 + (k % 4);
+      hi[idx] = tf32_hi(w);
+      lo[idx] = w - hi[idx];
+    }
+}
+inline void tc_pack_weights(const ConstParams& p, unsigned char* blob /*kTcBlobBytes*/) {
+  tc_pack_layer(p.W1, kNFeat, kH1, kTcK1, kTcN1, reinterpret_cast<float*>(blob + kTcOff1),
+                reinterpret_cast<float*>(blob + kTcOff1 + kTcBlk1));
+  tc_pack_layer(p.W2, kH1, kH2, kTcK2, kTcN2, reinterpret_cast<float*>(blob + kTcOff2),
+                reinterpret_cast<float*>(blob + kTcOff2 + kTcBlk2));
+  tc_pack_layer(p.W3, kH2, kH3, kTcK3, kTcN3, reinterpret_cast<float*>(blob + kTcOff3),
+                reinterpret_cast<float*>(blob + kTcOff3 + kTcBlk3));
+  tc_pack_layer(p.W4, kH3, kNCls, kTcK4, kTcN4, reinterpret_cast<float*>(blob + kTcOff4),
+                reinterpret_cast<float*>(blob + kTcOff4 + kTcBlk4));
+}
+
+#if defined(__CUDACC__)
+// ---- PTX wrappers ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tc_smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {  // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(
+          taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T, M = 128, kind::tf32 (K = 8 per instruction); one thread issues.
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {  // implies tcgen05.fence::before_thread_sync
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool tc_mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(tc_smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!tc_mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void tc_bar_128() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout)
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;  // descriptor version for sm_100
+  return d;
+}
+__host__ __device__ constexpr uint32_t tc_idesc(int n) {
+  return (1u << 4) /* D = f32 */ | (2u << 7) /* A = tf32 */ | (2u << 10) /* B = tf32 */ |
+         (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+}
+
+// One layer: 3 MMAs per k-step (hi.hi, lo.hi, hi.lo); executed by ONE thread.
+template <int K, int N>
+__device__ __forceinline__ void tc_issue_layer(uint32_t tm_base, uint32_t d_col, uint32_t w_smem /*hi block*/,
+                                               uint64_t* done_bar) {
+  constexpr uint32_t lbo = (N / 8) * 128, sbo = 128, blk = K * N * 4;
+  constexpr uint32_t idesc = tc_idesc(N);
+  const uint32_t a_hi = tm_base + kTmA, a_lo = tm_base + kTmA + K, d = tm_base + d_col;
+#pragma unroll
+  for (int j = 0; j < K / 8; ++j) {
+    const uint64_t b_hi = tc_smem_desc(w_smem + 2 * j * lbo, lbo, sbo);
+    const uint64_t b_lo = tc_smem_desc(w_smem + blk + 2 * j * lbo, lbo, sbo);
+    umma_tf32_ts(d, a_lo + 8 * j, b_hi, idesc, j > 0 ? 1u : 0u);
+    umma_tf32_ts(d, a_hi + 8 * j, b_lo, idesc, 1u);
+    umma_tf32_ts(d, a_hi + 8 * j, b_hi, idesc, 1u);
+  }
+  umma_commit(done_bar);
+}
+
+__device__ __forceinline__ void tc_split(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+// Epilogue of a hidden layer: D (NOUT fp32 columns at d_col) -> + bias, ReLU, hi/lo split -> A operand
+// of the next layer (hi at [0,NOUT), lo at [NOUT,2 NOUT)).  All 128 threads.
+template <int NOUT>
+__device__ __forceinline__ void tc_hidden_epilogue(uint32_t tm_lane_base, uint32_t d_col, const float* bias) {
+#pragma unroll
+  for (int c0 = 0; c0 < NOUT; c0 += 16) {
+    uint32_t v[16], hi[16], lo[16];
+    tmem_ld16(tm_lane_base + d_col + c0, v);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float a = fmaxf(__uint_as_float(v[i]) + bias[c0 + i], 0.0f);
+      tc_split(a, hi[i], lo[i]);
+    }
+    tmem_st16(tm_lane_base + kTmA + c0, hi);
+    tmem_st16(tm_lane_base + kTmA + NOUT + c0, lo);
+  }
+  tmem_wait_st();
+}
+
+// The whole FFN for one 128-frame tile.  Called by 128 threads (4 consecutive warps, `wq` = warp % 4,
+// `is_issuer` true for exactly one of them); x = 39 features of this thread's frame.
+// w_smem: shared-memory address of the weight blob (already landed); mma_bar: mbarrier (count 1) whose
+// current phase parity is `par` (toggled 4 times here, returned updated).
+__device__ __forceinline__ uint32_t ffn_tc_tile(const float (&x)[kNFeat], float (&logit)[kNCls], uint32_t tm_base,
+                                                int wq, bool is_issuer, uint32_t w_smem, uint64_t* mma_bar,
+                                                uint32_t par) {
+  const uint32_t tl = tm_base + (static_cast<uint32_t>(32 * wq) << 16);
+  // ---- A1 = split(x), K padded 39 -> 40
+#pragma unroll
+  for (int c0 = 0; c0 < 32; c0 += 16) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) tc_split(x[c0 + i], hi[i], lo[i]);
+    tmem_st16(tl + kTmA + c0, hi);
+    tmem_st16(tl + kTmA + kTcK1 + c0, lo);
+  }
+  {
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (32 + i < kNFeat) tc_split(x[32 + i], hi[i], lo[i]);
+      else hi[i] = lo[i] = 0u;
+    }
+    tmem_st8(tl + kTmA + 32, hi);
+    tmem_st8(tl + kTmA + kTcK1 + 32, lo);
+  }
+  tmem_wait_st();
+  tc_fence_before();
+  tc_bar_128();
+  if (is_issuer) {
+    tc_fence_after();
+    tc_issue_layer<kTcK1, kTcN1>(tm_base, kTmD1, w_smem + kTcOff1, mma_bar);
+  }
+  tc_mbar_wait(mma_bar, par); par ^= 1u;
+  tc_fence_after();
+  tc_hidden_epilogue<kTcN1>(tl, kTmD1, c_par.b1);
+  tc_fence_before();
+  tc_bar_128();
+  if (is_issuer) {
+    tc_fence_after();
+    tc_issue_layer<kTcK2, kTcN2>(tm_base, kTmD2, w_smem + kTcOff2, mma_bar);
+  }
+  tc_mbar_wait(mma_bar, par); par ^= 1u;
+  tc_fence_after();
+  tc_hidden_epilogue<kTcN2>(tl, kTmD2, c_par.b2);
+  tc_fence_before();
+  tc_bar_128();
+  if (is_issuer) {
+    tc_fence_after();
+    tc_issue_layer<kTcK3, kTcN3>(tm_base, kTmD3, w_smem + kTcOff3, mma_bar);
+  }
+  tc_mbar_wait(mma_bar, par); par ^= 1u;
+  tc_fence_after();
+  tc_hidden_epilogue<kTcN3>(tl, kTmD3, c_par.b3);
+  tc_fence_before();
+  tc_bar_128();
+  if (is_issuer) {
+    tc_fence_after();
+    tc_issue_layer<kTcK4, kTcN4>(tm_base, kTmD4, w_smem + kTcOff4, mma_bar);
+  }
+  tc_mbar_wait(mma_bar, par); par ^= 1u;
+  tc_fence_after();
+  {
+    uint32_t v[16];
+    tmem_ld16(tl + kTmD4, v);
+    tmem_wait_ld();
+#pragma unroll
+    for (int o = 0; o < kNCls; ++o) logit[o] = __uint_as_float(v[o]) + c_par.b4[o];
+  }
+  tc_fence_before();  // the next tile's tcgen05.st must not overtake these loads
+  return par;
+}
+#endif  // __CUDACC__
+
+}  // namespace vadb

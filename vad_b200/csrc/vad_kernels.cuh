@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 
 #include "vad_core.cuh"
+#include "ffn_tc.cuh"
 
 namespace vadb {
 
@@ -43,8 +44,10 @@ constexpr int kOffRing = kOffLogE + kNMel * 32 * 4;                         // +
 constexpr int kOffTw1 = kOffRing + kNCep * kRing * 4;                       // + 14976
 constexpr int kOffTw2 = kOffTw1 + 256 * 8;
 constexpr int kOffBar = kOffTw2 + 128 * 8;
-constexpr int kOffSeg = kOffBar + 16;
-constexpr int kFusedSmemBytes = kOffSeg + 16;
+constexpr int kOffSeg = kOffBar + 32;                                       // 4 mbarriers: pcm x2, weights, mma
+constexpr int kFusedSmemBytes = kOffSeg + 16;                               // s_seg, s_tmem
+constexpr int kBlockStepsTc = 4;                                            // tensor-core FFN: one M=128 tile
+static_assert(kTcBlobBytes <= kWarps * 2 * kExchFrame * 8 + kBins * kPPitch * 4, "weight blob must fit exch + P");
 
 struct Segment {
   long long pcm_start;  // sample index of the first frame's first sample (multiple of 8)
@@ -67,6 +70,7 @@ struct FusedParams {
   float* rows;
   long long row_base;     // subtracted from Segment::out_start (chunked host runs)
   int feat_mode;
+  const unsigned char* tc_blob;  // canonical hi/lo tf32 weight blob (ffn_tc.cuh), TC variant only
 };
 
 // ---- PTX wrappers: mbarrier + TMA bulk copy (UBLKCP) --------------------------------------------
@@ -153,8 +157,12 @@ __device__ __forceinline__ void classify_row(const float (&r)[5][kNCep], int fea
   }
 }
 
-template <int MODE>  // 0: MFCC rows [T][13]; 1: dataset rows [T-5][39]; 2: VAD labels [T-5]
+// MODE 0: MFCC rows [T][13]; 1: dataset rows [T-5][39]; 2: VAD labels [T-5].
+// TC (MODE 2 only): 0 = FFN on FP32 CUDA cores, 1 = FFN on tcgen05 (tf32 x3, TMEM accumulators).
+template <int MODE, int TC>
 __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p) {
+  static_assert(TC == 0 || MODE == 2, "tensor-core FFN only exists in VAD mode");
+  constexpr int kBlk = TC ? kBlockStepsTc : kBlockSteps;
   extern __shared__ __align__(128) unsigned char smem[];
   int16_t* s_pcm = reinterpret_cast<int16_t*>(smem + kOffPcm);
   cf2* s_exch = reinterpret_cast<cf2*>(smem + kOffExch);
@@ -170,10 +178,21 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
 
   s_tw1[tid] = p.tw1[tid];
   if (tid < 128) s_tw2[tid] = p.tw2[tid];
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kOffSeg + 8);
   if (tid == 0) {
     mbar_init(&s_bar[0], 1);
     mbar_init(&s_bar[1], 1);
+    mbar_init(&s_bar[2], 1);
+    mbar_init(&s_bar[3], 1);
     fence_mbar_init();
+  }
+  uint32_t tm_base = 0, w_par = 0, mma_par = 0;
+  if (TC) {
+    if (warp == 0) tmem_alloc(s_tmem, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    tm_base = *s_tmem;
   }
 
   unsigned gstep = 0;  // loads issued so far by this CTA == steps started; buffer = gstep & 1
@@ -235,7 +254,8 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
       }
 
       const int computed = min((s + 1) * kStepFrames, n);
-      if (((s + 1) % kBlockSteps) == 0 || s == nsteps - 1) {
+      if (((s + 1) % kBlk) == 0 || s == nsteps - 1) {
+        if (TC) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // exch/P: generic writes before TMA overwrite
         __syncthreads();
         if (MODE == 0) {
           const long long base = (seg.out_start - p.row_base + out_done) * kNCep;
@@ -262,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
             p.rows[base + j] = v;
           }
           out_done = max(out_done, last + 1);
-        } else {
+        } else if (!TC) {
           const int c = out_done + tid;
           if (c <= computed - 3) {
             float r[5][kNCep];
@@ -275,10 +295,113 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
             classify_row(r, p.feat_mode, p.labels, p.logits, p.feats, seg.out_start - p.row_base + (c - 2));
           }
           out_done = max(out_done, computed - 2);
+        } else {
+          // ---- tensor-core FFN: one M = 128 tile, warps 0-3 (thread = frame = TMEM lane) --------
+          const int n_valid = computed - 2 - out_done;  // centres out_done .. computed-3 (<= 128)
+          if (n_valid > 0) {                            // block-uniform
+            unsigned char* wdst = smem + kOffExch;      // exch + P are idle during the block phase
+            if (tid == 0) {
+              mbar_arrive_expect_tx(&s_bar[2], kTcBlobBytes);
+              bulk_g2s(wdst, p.tc_blob, kTcBlobBytes, &s_bar[2]);
+            }
+            if (warp < 4) {
+              const bool valid = tid < n_valid;
+              const int c = out_done + (valid ? tid : 0);
+              float r[5][kNCep];
+#pragma unroll
+              for (int d = 0; d < 5; ++d) {
+                const int col = (c - 2 + d) % kRing;
+#pragma unroll
+                for (int k = 0; k < kNCep; ++k) r[d][k] = s_ring[k * kRing + col];
+              }
+              float x[kNFeat], logit[kNCls];
+              const bool ok = window_features(r, p.feat_mode, x);
+              mbar_wait(&s_bar[2], w_par);              // weight blob landed
+              mma_par = ffn_tc_tile(x, logit, tm_base, warp, tid == 0, smem_u32(wdst), &s_bar[3], mma_par);
+              if (valid) {
+                uint8_t lab = decide(logit);
+                if (!ok) {
+                  logit[0] = logit[1] = logit[2] = NAN;
+                  lab = 0;
+                }
+                const long long row = seg.out_start - p.row_base + (c - 2);
+                p.labels[row] = lab;
+                if (p.logits) {
+                  p.logits[row * 3 + 0] = logit[0];
+                  p.logits[row * 3 + 1] = logit[1];
+                  p.logits[row * 3 + 2] = logit[2];
+                }
+                if (p.feats) {
+#pragma unroll
+                  for (int i = 0; i < kNFeat; ++i) p.feats[row * kNFeat + i] = x[i];
+                }
+              }
+            }
+            w_par ^= 1u;
+            __syncthreads();  // MMAs done reading the blob before the next FFT phase rewrites exch / P
+          }
+          out_done = max(out_done, computed - 2);
         }
       }
     }
   }
+  if (TC) {
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tm_base, kTmemCols);
+  }
+}
+
+// Stand-alone tensor-core FFN over feature rows [n][39] (classifier.predict duck type): one CTA =
+// one 128-row tile.  Same tile routine as the fused kernel's block phase.
+constexpr int kFfnTcSmemBytes = kTcBlobBytes + 64;
+__global__ void __launch_bounds__(128) ffn_tc_rows_kernel(const float* x, long long n, const unsigned char* blob,
+                                                          uint8_t* labels, float* logits) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcBlobBytes);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kTcBlobBytes + 32);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(s_tmem, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tm_base = *s_tmem;
+  if (tid == 0) {
+    mbar_arrive_expect_tx(&bars[0], kTcBlobBytes);
+    bulk_g2s(smem, blob, kTcBlobBytes, &bars[0]);
+  }
+  const long long i = static_cast<long long>(blockIdx.x) * 128 + tid;
+  const long long src = i < n ? i : n - 1;
+  float v[kNFeat], logit[kNCls];
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < kNFeat; ++k) {
+    v[k] = x[src * kNFeat + k];
+    ok = ok && (fabsf(v[k]) <= 3.0e38f);
+  }
+  mbar_wait(&bars[0], 0);
+  ffn_tc_tile(v, logit, tm_base, warp, tid == 0, smem_u32(smem), &bars[1], 0);
+  if (i < n) {
+    uint8_t lab = decide(logit);
+    if (!ok) {
+      logit[0] = logit[1] = logit[2] = NAN;
+      lab = 0;
+    }
+    if (labels) labels[i] = lab;
+    if (logits) {
+      logits[i * 3 + 0] = logit[0];
+      logits[i * 3 + 1] = logit[1];
+      logits[i * 3 + 2] = logit[2];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tm_base, kTmemCols);
 }
 
 // ---- per-frame API kernels (explicit float32 frames; mfcc.py:59-78 one frame at a time) ----------

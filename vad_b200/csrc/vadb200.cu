@@ -67,6 +67,8 @@ struct vadb200_handle {
   float* d_lgt[kHostBufs] = {};
   long long stage_cap = 0, lab_cap = 0, lgt_cap = 0;
   float* d_sink = nullptr;
+  unsigned char* d_tc_blob = nullptr;  // canonical tf32 hi/lo weight blob (ffn_tc.cuh)
+  int ffn_impl = 0;                    // 0: FP32 CUDA cores, 1: tcgen05 tf32 x3
 };
 
 struct vadb200_plan {
@@ -107,9 +109,11 @@ int ensure_constants(vadb200_handle* h, cudaStream_t) {
 
 int ensure_attrs(vadb200_handle* h) {
   if (h->attr_set) return 0;
-  CU(cudaFuncSetAttribute(fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes));
-  CU(cudaFuncSetAttribute(fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes));
-  CU(cudaFuncSetAttribute(fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes));
+  CU(cudaFuncSetAttribute(fused_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes));
+  CU(cudaFuncSetAttribute(fused_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes));
+  CU(cudaFuncSetAttribute(fused_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes));
+  CU(cudaFuncSetAttribute(fused_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes));
+  CU(cudaFuncSetAttribute(ffn_tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnTcSmemBytes));
   CU(cudaFuncSetAttribute(frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFramesSmemBytes));
   CU(cudaFuncSetAttribute(stream_feed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes));
   h->attr_set = true;
@@ -126,9 +130,12 @@ int launch_fused(vadb200_plan* p, FusedParams fp, int n_segs, cudaStream_t st) {
   CU(cudaMemsetAsync(p->d_counter, 0, sizeof(int), st));
   const int grid = std::min(n_segs, 2 * h->num_sms);
   switch (p->mode) {
-    case VADB200_MODE_MFCC: fused_kernel<0><<<grid, kThreads, kFusedSmemBytes, st>>>(fp); break;
-    case VADB200_MODE_DATASET: fused_kernel<1><<<grid, kThreads, kFusedSmemBytes, st>>>(fp); break;
-    default: fused_kernel<2><<<grid, kThreads, kFusedSmemBytes, st>>>(fp); break;
+    case VADB200_MODE_MFCC: fused_kernel<0, 0><<<grid, kThreads, kFusedSmemBytes, st>>>(fp); break;
+    case VADB200_MODE_DATASET: fused_kernel<1, 0><<<grid, kThreads, kFusedSmemBytes, st>>>(fp); break;
+    default:
+      if (h->ffn_impl == 1) fused_kernel<2, 1><<<grid, kThreads, kFusedSmemBytes, st>>>(fp);
+      else fused_kernel<2, 0><<<grid, kThreads, kFusedSmemBytes, st>>>(fp);
+      break;
   }
   g_launches.fetch_add(1);
   CU(cudaGetLastError());
@@ -142,6 +149,7 @@ FusedParams base_params(vadb200_plan* p) {
   fp.counter = p->d_counter;
   fp.tw1 = p->h->d_tw;
   fp.tw2 = p->h->d_tw + 256;
+  fp.tc_blob = p->h->d_tc_blob;
   return fp;
 }
 
@@ -206,8 +214,10 @@ int vadb200_create(const vadb200_config* c, int device, vadb200_handle** out) {
   cudaError_t e = cudaMalloc(&h->d_tw, sizeof(tw));
   if (e == cudaSuccess) e = cudaMemcpy(h->d_tw, tw, sizeof(tw), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_sink, 256);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_tc_blob, kTcBlobBytes);
   if (e != cudaSuccess) {
     cudaFree(h->d_tw);
+    cudaFree(h->d_sink);
     delete h;
     return cuda_fail(e, "vadb200_create");
   }
@@ -229,6 +239,7 @@ int vadb200_destroy(vadb200_handle* h) {
   if (h->s_out) cudaStreamDestroy(h->s_out);
   cudaFree(h->d_tw);
   cudaFree(h->d_sink);
+  cudaFree(h->d_tc_blob);
   delete h;
   return 0;
 }
@@ -248,8 +259,21 @@ int vadb200_set_ffn_weights(vadb200_handle* h, const float* W1, const float* b1,
   std::memcpy(h->par.W4, W4, sizeof(h->par.W4)); std::memcpy(h->par.b4, b4, sizeof(h->par.b4));
   h->have_ffn = true;
   h->version = (h->version + 1) & 0xFFFFF;
+  // tensor-core operand blob; drained + blocking so kernels on any stream see a consistent copy
+  std::vector<unsigned char> blob(kTcBlobBytes);
+  tc_pack_weights(h->par, blob.data());
+  CU(cudaSetDevice(h->device));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(h->d_tc_blob, blob.data(), kTcBlobBytes, cudaMemcpyHostToDevice));
   return 0;
 }
+
+int vadb200_set_ffn_impl(vadb200_handle* h, int impl) {
+  if (!h || impl < 0 || impl > 1) return fail(VADB200_E_INVALID, "impl must be 0 (fp32) or 1 (tcgen05 tf32x3)");
+  h->ffn_impl = impl;
+  return 0;
+}
+int vadb200_get_ffn_impl(vadb200_handle* h) { return h ? h->ffn_impl : -1; }
 
 int vadb200_set_host_chunk_samples(vadb200_handle* h, int64_t samples) {
   if (!h || samples < 4096) return fail(VADB200_E_INVALID, "chunk must be >= 4096 samples");
@@ -542,7 +566,14 @@ int vadb200_ffn_predict(vadb200_handle* h, const float* d_x, int64_t n, uint8_t*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = ensure_constants(h, st);
   if (rc) return rc;
-  ffn_rows_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(d_x, n, d_labels, d_logits);
+  if (h->ffn_impl == 1) {
+    rc = ensure_attrs(h);
+    if (rc) return rc;
+    ffn_tc_rows_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, kFfnTcSmemBytes, st>>>(d_x, n, h->d_tc_blob,
+                                                                                                 d_labels, d_logits);
+  } else {
+    ffn_rows_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(d_x, n, d_labels, d_logits);
+  }
   g_launches.fetch_add(1);
   CU(cudaGetLastError());
   return 0;

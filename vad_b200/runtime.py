@@ -105,6 +105,15 @@ class Handle(object):
         check(self.lib.vadb200_set_ffn_weights(self._h, *[a.ctypes.data_as(C.c_void_p) for a in arrs]))
         self.has_ffn = True
 
+    def set_ffn_impl(self, impl):
+        """0 / "fp32": CUDA-core FFMA; 1 / "tc": tcgen05 tensor cores (tf32 x3, TMEM accumulators)."""
+        impl = {"fp32": 0, "tc": 1}.get(impl, impl)
+        check(self.lib.vadb200_set_ffn_impl(self._h, int(impl)))
+
+    @property
+    def ffn_impl(self):
+        return int(self.lib.vadb200_get_ffn_impl(self._h))
+
     # ---- per-frame API --------------------------------------------------------------------
     def _frames_tensor(self, frames):
         t = torch.as_tensor(np.asarray(frames, dtype=np.float32) if not torch.is_tensor(frames) else frames)
