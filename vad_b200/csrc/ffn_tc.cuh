@@ -110,6 +110,17 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]),
                "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
@@ -144,7 +155,6 @@ __device__ __forceinline__ void tc_mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!tc_mbar_try_wait(bar, parity)) {
   }
 }
-__device__ __forceinline__ void tc_bar_128() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout)
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -184,43 +194,75 @@ __device__ __forceinline__ void tc_split(float x, uint32_t& hi, uint32_t& lo) {
 }
 
 // Epilogue of a hidden layer: D (NOUT fp32 columns at d_col) -> + bias, ReLU, hi/lo split -> A operand
-// of the next layer (hi at [0,NOUT), lo at [NOUT,2 NOUT)).  All 128 threads.
-template <int NOUT>
-__device__ __forceinline__ void tc_hidden_epilogue(uint32_t tm_lane_base, uint32_t d_col, const float* bias) {
+// of the next layer (hi at [0,NOUT), lo at [NOUT,2 NOUT)).  With HALVES = 2 two threads share a frame
+// (warp w and w + 4 own the same TMEM lane quarter) and each converts NOUT/2 columns.
+template <int NOUT, int HALVES>
+__device__ __forceinline__ void tc_hidden_epilogue(uint32_t tl, uint32_t d_col, const float* bias, int hidx) {
+  constexpr int W = NOUT / HALVES;         // columns per thread: 64, 32, 16 or 8
+  constexpr int CH = W >= 16 ? 16 : 8;     // chunk width
+  const int base = hidx * W;
 #pragma unroll
-  for (int c0 = 0; c0 < NOUT; c0 += 16) {
-    uint32_t v[16], hi[16], lo[16];
-    tmem_ld16(tm_lane_base + d_col + c0, v);
+  for (int c0 = 0; c0 < W; c0 += CH) {
+    uint32_t v[CH], hi[CH], lo[CH];
+    if constexpr (CH == 16) tmem_ld16(tl + d_col + base + c0, v);
+    else tmem_ld8(tl + d_col + base + c0, v);
     tmem_wait_ld();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float a = fmaxf(__uint_as_float(v[i]) + bias[c0 + i], 0.0f);
+    for (int i = 0; i < CH; ++i) {
+      const float a = fmaxf(__uint_as_float(v[i]) + bias[base + c0 + i], 0.0f);
       tc_split(a, hi[i], lo[i]);
     }
-    tmem_st16(tm_lane_base + kTmA + c0, hi);
-    tmem_st16(tm_lane_base + kTmA + NOUT + c0, lo);
+    if constexpr (CH == 16) {
+      tmem_st16(tl + kTmA + base + c0, hi);
+      tmem_st16(tl + kTmA + NOUT + base + c0, lo);
+    } else {
+      tmem_st8(tl + kTmA + base + c0, hi);
+      tmem_st8(tl + kTmA + NOUT + base + c0, lo);
+    }
   }
   tmem_wait_st();
 }
 
-// The whole FFN for one 128-frame tile.  Called by 128 threads (4 consecutive warps, `wq` = warp % 4,
-// `is_issuer` true for exactly one of them); x = 39 features of this thread's frame.
-// w_smem: shared-memory address of the weight blob (already landed); mma_bar: mbarrier (count 1) whose
-// current phase parity is `par` (toggled 4 times here, returned updated).
+template <int HALVES>
+__device__ __forceinline__ void tc_bar() {
+  if constexpr (HALVES == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
+  else asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
+// The whole FFN for one 128-frame tile, executed by 128 * HALVES threads.  Thread (wq = warp % 4, lane)
+// owns TMEM lane 32 wq + lane = one frame; with HALVES = 2 the threads of warp w and w + 4 share that
+// frame (hidx = warp / 4) and split every layer's columns.  x = the frame's 39 features (both halves
+// hold them); logits are returned to hidx == 0.  w_smem: shared-memory address of the weight blob
+// (already landed); mma_bar: mbarrier (count 1) whose current phase parity is `par` (4 phases used).
+template <int HALVES>
 __device__ __forceinline__ uint32_t ffn_tc_tile(const float (&x)[kNFeat], float (&logit)[kNCls], uint32_t tm_base,
-                                                int wq, bool is_issuer, uint32_t w_smem, uint64_t* mma_bar,
-                                                uint32_t par) {
+                                                int wq, int hidx, bool is_issuer, uint32_t w_smem,
+                                                uint64_t* mma_bar, uint32_t par) {
   const uint32_t tl = tm_base + (static_cast<uint32_t>(32 * wq) << 16);
-  // ---- A1 = split(x), K padded 39 -> 40
+  // ---- A1 = split(x), K padded 39 -> 40; columns [20 hidx, 20 hidx + 20) when shared by two threads
+  if constexpr (HALVES == 2) {
+    const int b = 20 * hidx;
+    uint32_t hi[16], lo[16], hi4[4], lo4[4];
 #pragma unroll
-  for (int c0 = 0; c0 < 32; c0 += 16) {
-    uint32_t hi[16], lo[16];
+    for (int i = 0; i < 16; ++i) tc_split(hidx ? x[20 + i] : x[i], hi[i], lo[i]);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) tc_split(x[c0 + i], hi[i], lo[i]);
-    tmem_st16(tl + kTmA + c0, hi);
-    tmem_st16(tl + kTmA + kTcK1 + c0, lo);
-  }
-  {
+    for (int i = 0; i < 4; ++i) {
+      const float v = hidx ? (i < 3 ? x[36 + i] : 0.0f) : x[16 + i];
+      tc_split(v, hi4[i], lo4[i]);
+    }
+    tmem_st16(tl + kTmA + b, hi);
+    tmem_st4(tl + kTmA + b + 16, hi4);
+    tmem_st16(tl + kTmA + kTcK1 + b, lo);
+    tmem_st4(tl + kTmA + kTcK1 + b + 16, lo4);
+  } else {
+#pragma unroll
+    for (int c0 = 0; c0 < 32; c0 += 16) {
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) tc_split(x[c0 + i], hi[i], lo[i]);
+      tmem_st16(tl + kTmA + c0, hi);
+      tmem_st16(tl + kTmA + kTcK1 + c0, lo);
+    }
     uint32_t hi[8], lo[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -232,43 +274,43 @@ __device__ __forceinline__ uint32_t ffn_tc_tile(const float (&x)[kNFeat], float 
   }
   tmem_wait_st();
   tc_fence_before();
-  tc_bar_128();
+  tc_bar<HALVES>();
   if (is_issuer) {
     tc_fence_after();
     tc_issue_layer<kTcK1, kTcN1>(tm_base, kTmD1, w_smem + kTcOff1, mma_bar);
   }
   tc_mbar_wait(mma_bar, par); par ^= 1u;
   tc_fence_after();
-  tc_hidden_epilogue<kTcN1>(tl, kTmD1, c_par.b1);
+  tc_hidden_epilogue<kTcN1, HALVES>(tl, kTmD1, c_par.b1, hidx);
   tc_fence_before();
-  tc_bar_128();
+  tc_bar<HALVES>();
   if (is_issuer) {
     tc_fence_after();
     tc_issue_layer<kTcK2, kTcN2>(tm_base, kTmD2, w_smem + kTcOff2, mma_bar);
   }
   tc_mbar_wait(mma_bar, par); par ^= 1u;
   tc_fence_after();
-  tc_hidden_epilogue<kTcN2>(tl, kTmD2, c_par.b2);
+  tc_hidden_epilogue<kTcN2, HALVES>(tl, kTmD2, c_par.b2, hidx);
   tc_fence_before();
-  tc_bar_128();
+  tc_bar<HALVES>();
   if (is_issuer) {
     tc_fence_after();
     tc_issue_layer<kTcK3, kTcN3>(tm_base, kTmD3, w_smem + kTcOff3, mma_bar);
   }
   tc_mbar_wait(mma_bar, par); par ^= 1u;
   tc_fence_after();
-  tc_hidden_epilogue<kTcN3>(tl, kTmD3, c_par.b3);
+  tc_hidden_epilogue<kTcN3, HALVES>(tl, kTmD3, c_par.b3, hidx);
   tc_fence_before();
-  tc_bar_128();
+  tc_bar<HALVES>();
   if (is_issuer) {
     tc_fence_after();
     tc_issue_layer<kTcK4, kTcN4>(tm_base, kTmD4, w_smem + kTcOff4, mma_bar);
   }
   tc_mbar_wait(mma_bar, par); par ^= 1u;
   tc_fence_after();
-  {
-    uint32_t v[16];
-    tmem_ld16(tl + kTmD4, v);
+  if (hidx == 0) {
+    uint32_t v[8];
+    tmem_ld8(tl + kTmD4, v);
     tmem_wait_ld();
 #pragma unroll
     for (int o = 0; o < kNCls; ++o) logit[o] = __uint_as_float(v[o]) + c_par.b4[o];

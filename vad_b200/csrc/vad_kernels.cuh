@@ -244,7 +244,15 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
 
       // ---- mel + log phase -----------------------------------------------------------------
       mel_group_dispatch<kPPitch, 32>(warp, s_P + lane, s_logE + lane);
+      const int computed = min((s + 1) * kStepFrames, n);
+      const bool block_now = ((s + 1) % kBlk) == 0 || s == nsteps - 1;
+      const bool tc_now = TC && block_now && (computed - 2 - out_done) > 0;  // block-uniform
+      if (tc_now) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // exch/P generic accesses before the TMA overwrite
       __syncthreads();
+      if (tc_now && tid == 0) {  // exch + P are idle until the next FFT phase: land the weight blob during the DCT
+        mbar_arrive_expect_tx(&s_bar[2], kTcBlobBytes);
+        bulk_g2s(smem + kOffExch, p.tc_blob, kTcBlobBytes, &s_bar[2]);
+      }
 
       // ---- DCT phase -> MFCC ring -----------------------------------------------------------
       {
@@ -253,9 +261,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
         if (warp + 8 < kNCep) s_ring[(warp + 8) * kRing + col] = dct_coef<32>(s_logE + lane, warp + 8);
       }
 
-      const int computed = min((s + 1) * kStepFrames, n);
-      if (((s + 1) % kBlk) == 0 || s == nsteps - 1) {
-        if (TC) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // exch/P: generic writes before TMA overwrite
+      if (block_now) {
         __syncthreads();
         if (MODE == 0) {
           const long long base = (seg.out_start - p.row_base + out_done) * kNCep;
@@ -296,15 +302,13 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
           }
           out_done = max(out_done, computed - 2);
         } else {
-          // ---- tensor-core FFN: one M = 128 tile, warps 0-3 (thread = frame = TMEM lane) --------
+          // ---- tensor-core FFN: one M = 128 tile, warps 0-3 (thread = frame = TMEM lane).  Splitting each
+          // layer's columns over all 8 warps (ffn_tc_tile<2>) was measured slower (237 vs 228 ms / 1000 h):
+          // the phase is a latency chain, not epilogue-throughput bound. -----------------------------------
           const int n_valid = computed - 2 - out_done;  // centres out_done .. computed-3 (<= 128)
-          if (n_valid > 0) {                            // block-uniform
-            unsigned char* wdst = smem + kOffExch;      // exch + P are idle during the block phase
-            if (tid == 0) {
-              mbar_arrive_expect_tx(&s_bar[2], kTcBlobBytes);
-              bulk_g2s(wdst, p.tc_blob, kTcBlobBytes, &s_bar[2]);
-            }
-            if (warp < 4) {
+          if (n_valid > 0) {                            // block-uniform (== tc_now)
+            unsigned char* wdst = smem + kOffExch;
+            if (warp < 4) {  // warps 4-7 wait at the closing barrier; the co-resident CTA fills the SM
               const bool valid = tid < n_valid;
               const int c = out_done + (valid ? tid : 0);
               float r[5][kNCep];
@@ -316,8 +320,8 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
               }
               float x[kNFeat], logit[kNCls];
               const bool ok = window_features(r, p.feat_mode, x);
-              mbar_wait(&s_bar[2], w_par);              // weight blob landed
-              mma_par = ffn_tc_tile(x, logit, tm_base, warp, tid == 0, smem_u32(wdst), &s_bar[3], mma_par);
+              mbar_wait(&s_bar[2], w_par);              // weight blob landed (issued before the DCT phase)
+              mma_par = ffn_tc_tile<1>(x, logit, tm_base, warp, 0, tid == 0, smem_u32(wdst), &s_bar[3], mma_par);
               if (valid) {
                 uint8_t lab = decide(logit);
                 if (!ok) {
@@ -385,7 +389,7 @@ __global__ void __launch_bounds__(128) ffn_tc_rows_kernel(const float* x, long l
     ok = ok && (fabsf(v[k]) <= 3.0e38f);
   }
   mbar_wait(&bars[0], 0);
-  ffn_tc_tile(v, logit, tm_base, warp, tid == 0, smem_u32(smem), &bars[1], 0);
+  ffn_tc_tile<1>(v, logit, tm_base, warp, 0, tid == 0, smem_u32(smem), &bars[1], 0);
   if (i < n) {
     uint8_t lab = decide(logit);
     if (!ok) {
