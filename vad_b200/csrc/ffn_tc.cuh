@@ -13,7 +13,7 @@
 //
 // One tile = 128 frames = 128 threads (4 warps; warp w owns TMEM lanes 32 (w % 4) ..+31, thread =
 // frame = lane).  TMEM map (256 columns per CTA, 2 CTAs per SM = all 512):
-//   [  0,128)  A operand of the current layer: hi in [0,K), lo in [K,2K)   (K = 40, 64, 32, 16)
+//   [  0,128)  A operand of the current layer: hi in [0,K), lo in [K,2K)   (K = 48, 64, 32, 16)
 //   [128,192)  D1 (64)  -> later D3 [128,144) and D4 [144,160)
 //   [192,224)  D2 (32)
 // Weights (B operand, N x K, K-major, SWIZZLE_NONE canonical layout: 8x16B core matrices,
@@ -30,7 +30,14 @@
 
 namespace vadb {
 
-constexpr int kTcK1 = 40, kTcN1 = 64;   // 39 -> 40 (k multiple of 8), 64
+constexpr int kTcK1 = 48, kTcN1 = 64;   // 39 -> 48: two 24-column halves (coefficients 0-6 | 7-12), see tc_feat_col
+// Layer-1 K order: feature (g, k) (g = 0 z, 1 d1, 2 d2; reference order g*13 + k) sits in column
+// 3k + g for k < 7 and 24 + 3(k-7) + g for k >= 7, so that the two threads sharing a frame can each
+// build the features of one coefficient range and store one contiguous 24-column block.
+__host__ __device__ constexpr int tc_feat_col(int feat) {
+  const int g = feat / 13, k = feat % 13;
+  return k < 7 ? 3 * k + g : 24 + 3 * (k - 7) + g;
+}
 constexpr int kTcK2 = 64, kTcN2 = 32;
 constexpr int kTcK3 = 32, kTcN3 = 16;
 constexpr int kTcK4 = 16, kTcN4 = 16;   // 3 -> 16 (M = 128 needs N % 16 == 0)
@@ -40,7 +47,7 @@ constexpr int kTcOff1 = 0;
 constexpr int kTcOff2 = kTcOff1 + 2 * kTcBlk1;
 constexpr int kTcOff3 = kTcOff2 + 2 * kTcBlk2;
 constexpr int kTcOff4 = kTcOff3 + 2 * kTcBlk3;
-constexpr int kTcBlobBytes = kTcOff4 + 2 * kTcBlk4;  // 43,008
+constexpr int kTcBlobBytes = kTcOff4 + 2 * kTcBlk4;  // 47,104
 constexpr int kTmemCols = 256;
 constexpr int kTmA = 0, kTmD1 = 128, kTmD3 = 128, kTmD4 = 144, kTmD2 = 192;
 
@@ -54,11 +61,12 @@ inline float tf32_hi(float x) {
   return r;
 }
 inline void tc_pack_layer(const float* W /*[k_real][n_real]*/, int k_real, int n_real, int K, int N, float* hi,
-                          float* lo) {
+                          float* lo, bool permute_features = false) {
   for (int i = 0; i < K * N; ++i) hi[i] = lo[i] = 0.0f;
   for (int n = 0; n < n_real; ++n)
-    for (int k = 0; k < k_real; ++k) {
-      const float w = W[k * n_real + n];
+    for (int kk = 0; kk < k_real; ++kk) {
+      const float w = W[kk * n_real + n];
+      const int k = permute_features ? tc_feat_col(kk) : kk;
       const int idx = ((k / 4) * (N / 8) + (n / 8)) * 32 + (n % 8) * 4 + (k % 4);
       hi[idx] = tf32_hi(w);
       lo[idx] = w - hi[idx];
@@ -66,7 +74,7 @@ inline void tc_pack_layer(const float* W /*[k_real][n_real]*/, int k_real, int n
 }
 inline void tc_pack_weights(const ConstParams& p, unsigned char* blob /*kTcBlobBytes*/) {
   tc_pack_layer(p.W1, kNFeat, kH1, kTcK1, kTcN1, reinterpret_cast<float*>(blob + kTcOff1),
-                reinterpret_cast<float*>(blob + kTcOff1 + kTcBlk1));
+                reinterpret_cast<float*>(blob + kTcOff1 + kTcBlk1), true);
   tc_pack_layer(p.W2, kH1, kH2, kTcK2, kTcN2, reinterpret_cast<float*>(blob + kTcOff2),
                 reinterpret_cast<float*>(blob + kTcOff2 + kTcBlk2));
   tc_pack_layer(p.W3, kH2, kH3, kTcK3, kTcN3, reinterpret_cast<float*>(blob + kTcOff3),
@@ -229,49 +237,30 @@ __device__ __forceinline__ void tc_bar() {
   else asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
+// Store 24 layer-1 A columns (one half: hidx = 0 -> columns [0,24), 1 -> [24,48)) of this thread's frame.
+__device__ __forceinline__ void tc_store_a1_half(uint32_t tl, int hidx, const float (&xl)[24]) {
+  uint32_t hi[16], lo[16], hi8[8], lo8[8];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) tc_split(xl[i], hi[i], lo[i]);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tc_split(xl[16 + i], hi8[i], lo8[i]);
+  const uint32_t b = tl + kTmA + 24 * hidx;
+  tmem_st16(b, hi);
+  tmem_st8(b + 16, hi8);
+  tmem_st16(b + kTcK1, lo);
+  tmem_st8(b + kTcK1 + 16, lo8);
+}
+
 // The whole FFN for one 128-frame tile, executed by 128 * HALVES threads.  Thread (wq = warp % 4, lane)
 // owns TMEM lane 32 wq + lane = one frame; with HALVES = 2 the threads of warp w and w + 4 share that
-// frame (hidx = warp / 4) and split every layer's columns.  x = the frame's 39 features (both halves
-// hold them); logits are returned to hidx == 0.  w_smem: shared-memory address of the weight blob
-// (already landed); mma_bar: mbarrier (count 1) whose current phase parity is `par` (4 phases used).
+// frame (hidx = warp / 4): each has already stored its half of the layer-1 A operand
+// (tc_store_a1_half) and they split every later layer's columns.  With HALVES = 1 the single thread
+// stored both halves.  Logits are returned to hidx == 0.  w_smem: shared-memory address of the weight
+// blob (already landed); mma_bar: mbarrier (count 1) whose current phase parity is `par` (4 phases).
 template <int HALVES>
-__device__ __forceinline__ uint32_t ffn_tc_tile(const float (&x)[kNFeat], float (&logit)[kNCls], uint32_t tm_base,
-                                                int wq, int hidx, bool is_issuer, uint32_t w_smem,
-                                                uint64_t* mma_bar, uint32_t par) {
+__device__ __forceinline__ uint32_t ffn_tc_tile(float (&logit)[kNCls], uint32_t tm_base, int wq, int hidx,
+                                                bool is_issuer, uint32_t w_smem, uint64_t* mma_bar, uint32_t par) {
   const uint32_t tl = tm_base + (static_cast<uint32_t>(32 * wq) << 16);
-  // ---- A1 = split(x), K padded 39 -> 40; columns [20 hidx, 20 hidx + 20) when shared by two threads
-  if constexpr (HALVES == 2) {
-    const int b = 20 * hidx;
-    uint32_t hi[16], lo[16], hi4[4], lo4[4];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) tc_split(hidx ? x[20 + i] : x[i], hi[i], lo[i]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float v = hidx ? (i < 3 ? x[36 + i] : 0.0f) : x[16 + i];
-      tc_split(v, hi4[i], lo4[i]);
-    }
-    tmem_st16(tl + kTmA + b, hi);
-    tmem_st4(tl + kTmA + b + 16, hi4);
-    tmem_st16(tl + kTmA + kTcK1 + b, lo);
-    tmem_st4(tl + kTmA + kTcK1 + b + 16, lo4);
-  } else {
-#pragma unroll
-    for (int c0 = 0; c0 < 32; c0 += 16) {
-      uint32_t hi[16], lo[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) tc_split(x[c0 + i], hi[i], lo[i]);
-      tmem_st16(tl + kTmA + c0, hi);
-      tmem_st16(tl + kTmA + kTcK1 + c0, lo);
-    }
-    uint32_t hi[8], lo[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (32 + i < kNFeat) tc_split(x[32 + i], hi[i], lo[i]);
-      else hi[i] = lo[i] = 0u;
-    }
-    tmem_st8(tl + kTmA + 32, hi);
-    tmem_st8(tl + kTmA + kTcK1 + 32, lo);
-  }
   tmem_wait_st();
   tc_fence_before();
   tc_bar<HALVES>();

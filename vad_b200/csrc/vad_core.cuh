@@ -314,6 +314,36 @@ VADB_HD bool window_features(const float (&r)[5][kNCep], int mode, float (&x)[kN
   return ok;
 }
 
+// Features of the coefficient range [K0, K1) only, ordered (k, g): out[3 (k-K0) + g] with g = 0 z,
+// 1 d1, 2 d2 -- the layer-1 column order of the tensor-core FFN (ffn_tc.cuh: tc_feat_col).
+// ring: MFCC ring [coef][RING]; centre frame c.  Same arithmetic as window_features.
+template <int K0, int K1, int RING, int NOUT>
+VADB_HD bool window_features_range(const float* ring, int c, int mode, float (&out)[NOUT]) {
+  bool ok = true;
+  static_assert(3 * (K1 - K0) <= NOUT, "output too small");
+  const int c0i = (c - 2) % RING, c1i = (c - 1) % RING, c2i = c % RING, c3i = (c + 1) % RING, c4i = (c + 2) % RING;
+#pragma unroll
+  for (int k = K0; k < K1; ++k) {
+    const float* row = ring + k * RING;
+    const float c0 = row[c0i], c1 = row[c1i], c2 = row[c2i], c3 = row[c3i], c4 = row[c4i];
+    float z = c2;
+    if (mode == 0) {
+      const float mu = ((((c0 + c1) + c2) + c3) + c4) * 0.2f;
+      const float d0 = c0 - mu, d1 = c1 - mu, d2 = c2 - mu, d3 = c3 - mu, d4 = c4 - mu;
+      const float var = fmaf(d4, d4, fmaf(d3, d3, fmaf(d2, d2, fmaf(d1, d1, d0 * d0)))) * 0.2f;
+      const bool alleq = (c0 == c1) && (c1 == c2) && (c2 == c3) && (c3 == c4);
+      z = alleq ? NAN : d2 / sqrtf(var);
+      ok = ok && (fabsf(z) <= 3.0e38f);
+    }
+    out[3 * (k - K0) + 0] = z;
+    out[3 * (k - K0) + 1] = c3 - c1;
+    out[3 * (k - K0) + 2] = (c4 - z) - (z - c0);
+  }
+#pragma unroll
+  for (int i = 3 * (K1 - K0); i < NOUT; ++i) out[i] = 0.0f;
+  return ok;
+}
+
 // ---- FFN forward, one frame per thread, weights as uniform constant operands -------------------
 VADB_HD void ffn_forward(const float (&x)[kNFeat], float (&logit)[kNCls]) {
   float h2[kH2];

@@ -302,27 +302,35 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
           }
           out_done = max(out_done, computed - 2);
         } else {
-          // ---- tensor-core FFN: one M = 128 tile, warps 0-3 (thread = frame = TMEM lane).  Splitting each
-          // layer's columns over all 8 warps (ffn_tc_tile<2>) was measured slower (237 vs 228 ms / 1000 h):
-          // the phase is a latency chain, not epilogue-throughput bound. -----------------------------------
+          // ---- tensor-core FFN: one M = 128 tile over all 8 warps ------------------------------------
           const int n_valid = computed - 2 - out_done;  // centres out_done .. computed-3 (<= 128)
           if (n_valid > 0) {                            // block-uniform (== tc_now)
             unsigned char* wdst = smem + kOffExch;
-            if (warp < 4) {  // warps 4-7 wait at the closing barrier; the co-resident CTA fills the SM
-              const bool valid = tid < n_valid;
-              const int c = out_done + (valid ? tid : 0);
-              float r[5][kNCep];
+            {
+              // thread (warp % 4, lane) = frame = TMEM lane; the two threads sharing a frame (hidx = warp / 4)
+              // build the features of cepstral coefficients 0-6 / 7-12 and split every layer's columns.
+              const int fr = tid & 127, hidx = tid >> 7;
+              const bool valid = fr < n_valid;
+              const int c = out_done + (valid ? fr : 0);
+              const uint32_t tl = tm_base + (static_cast<uint32_t>(32 * (warp & 3)) << 16);
+              float xl[24], logit[kNCls];
+              // the half's validity flag travels through shared memory (logE is idle here): ReLU's fmaxf
+              // swallows NaNs, so validity cannot be read back from the logits
+              const bool ok_half = (hidx == 0) ? window_features_range<0, 7, kRing, 24>(s_ring, c, p.feat_mode, xl)
+                                               : window_features_range<7, 13, kRing, 24>(s_ring, c, p.feat_mode, xl);
+              s_logE[tid] = ok_half ? 1.0f : 0.0f;
+              tc_store_a1_half(tl, hidx, xl);
+              if (p.feats && valid) {
+                const long long row = seg.out_start - p.row_base + (c - 2);
+                const int k0 = hidx ? 7 : 0, nk = hidx ? 6 : 7;
+                for (int k = 0; k < nk; ++k)
 #pragma unroll
-              for (int d = 0; d < 5; ++d) {
-                const int col = (c - 2 + d) % kRing;
-#pragma unroll
-                for (int k = 0; k < kNCep; ++k) r[d][k] = s_ring[k * kRing + col];
+                  for (int g = 0; g < 3; ++g) p.feats[row * kNFeat + g * kNCep + k0 + k] = xl[3 * k + g];
               }
-              float x[kNFeat], logit[kNCls];
-              const bool ok = window_features(r, p.feat_mode, x);
               mbar_wait(&s_bar[2], w_par);              // weight blob landed (issued before the DCT phase)
-              mma_par = ffn_tc_tile<1>(x, logit, tm_base, warp, 0, tid == 0, smem_u32(wdst), &s_bar[3], mma_par);
-              if (valid) {
+              mma_par = ffn_tc_tile<2>(logit, tm_base, warp & 3, hidx, tid == 0, smem_u32(wdst), &s_bar[3], mma_par);
+              if (valid && hidx == 0) {
+                const bool ok = s_logE[fr] != 0.0f && s_logE[128 + fr] != 0.0f;  // ordered by the tile's bar.syncs
                 uint8_t lab = decide(logit);
                 if (!ok) {
                   logit[0] = logit[1] = logit[2] = NAN;
@@ -334,10 +342,6 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
                   p.logits[row * 3 + 0] = logit[0];
                   p.logits[row * 3 + 1] = logit[1];
                   p.logits[row * 3 + 2] = logit[2];
-                }
-                if (p.feats) {
-#pragma unroll
-                  for (int i = 0; i < kNFeat; ++i) p.feats[row * kNFeat + i] = x[i];
                 }
               }
             }
@@ -389,7 +393,23 @@ __global__ void __launch_bounds__(128) ffn_tc_rows_kernel(const float* x, long l
     ok = ok && (fabsf(v[k]) <= 3.0e38f);
   }
   mbar_wait(&bars[0], 0);
-  ffn_tc_tile<1>(v, logit, tm_base, warp, 0, tid == 0, smem_u32(smem), &bars[1], 0);
+  {
+    const uint32_t tl = tm_base + (static_cast<uint32_t>(32 * warp) << 16);
+    float h0[24], h1[24];
+#pragma unroll
+    for (int i = 0; i < 24; ++i) h0[i] = h1[i] = 0.0f;
+#pragma unroll
+    for (int f = 0; f < kNFeat; ++f) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int col = tc_feat_col(f);
+      if (col < 24) h0[col] = v[f];
+      else h1[col - 24] = v[f];
+    }
+    tc_store_a1_half(tl, 0, h0);
+    tc_store_a1_half(tl, 1, h1);
+  }
+  ffn_tc_tile<1>(logit, tm_base, warp, 0, tid == 0, smem_u32(smem), &bars[1], 0);
   if (i < n) {
     uint8_t lab = decide(logit);
     if (!ok) {

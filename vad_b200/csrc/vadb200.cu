@@ -68,7 +68,7 @@ struct vadb200_handle {
   long long stage_cap = 0, lab_cap = 0, lgt_cap = 0;
   float* d_sink = nullptr;
   unsigned char* d_tc_blob = nullptr;  // canonical tf32 hi/lo weight blob (ffn_tc.cuh)
-  int ffn_impl = 0;                    // 0: FP32 CUDA cores, 1: tcgen05 tf32 x3
+  int ffn_impl = 1;                    // 0: FP32 CUDA cores, 1: tcgen05 tf32 x3 (default)
 };
 
 struct vadb200_plan {
