@@ -161,17 +161,23 @@ VADB_HD void fft_load_f32(const float* fr, int frame_len, int t, float (&xr)[16]
   });
 }
 
-// tw1: [k1][t] = W256^(t k1)
-template <int NZ>
-VADB_HD void fft_pass1(float (&xr)[16], float (&xi)[16], const cf2* tw1, int t) {
+// tw1: [k1][t] = W256^(t k1).  TW1 is a callable (k1 -> cf2): shared-memory table reads in the
+// emulation / small kernels, per-thread register copies in the fused kernel (the table rows depend
+// only on t, and re-reading them every round was 25 % of the kernel's shared-memory traffic).
+template <int NZ, class TW1>
+VADB_HD void fft_pass1_tw(float (&xr)[16], float (&xi)[16], TW1&& tw1) {
   dft16<NZ>(xr, xi);
   static_for<1, 16>([&](auto K) {
     constexpr int k1 = K;
-    const cf2 w = tw1[k1 * 16 + t];
+    const cf2 w = tw1(K);
     const float r = xr[k1], i = xi[k1];
     xr[k1] = fmaf(r, w.x, -(i * w.y));
     xi[k1] = fmaf(r, w.y, i * w.x);
   });
+}
+template <int NZ>
+VADB_HD void fft_pass1(float (&xr)[16], float (&xi)[16], const cf2* tw1, int t) {
+  fft_pass1_tw<NZ>(xr, xi, [&](auto K) { return tw1[decltype(K)::value * 16 + t]; });
 }
 
 // 16x16 transpose buffer of one frame: row n2 = t (pass-1 thread), column k1; row pitch 17
@@ -215,9 +221,9 @@ VADB_HD void split_pair(float ar, float ai, float br, float bi, float wr, float 
 #if defined(__CUDACC__)
 #pragma nv_exec_check_disable
 #endif
-template <class XCH, class STORE>
-VADB_HD void fft_split_store(const float (&xr)[16], const float (&xi)[16], int k1, const cf2* tw2,
-                             XCH&& xch, STORE&& store) {
+template <class TW2, class XCH, class STORE>
+VADB_HD void fft_split_store_tw(const float (&xr)[16], const float (&xi)[16], int k1, TW2&& tw2,
+                                XCH&& xch, STORE&& store) {
   float sr[16], si[16];
   static_for<8, 16>([&](auto J) {
     constexpr int j = J;
@@ -229,7 +235,7 @@ VADB_HD void fft_split_store(const float (&xr)[16], const float (&xi)[16], int k
     constexpr int k2 = K;
     const float br = xch(sr[15 - k2], 15 - k2, false, partner);
     const float bi = xch(si[15 - k2], 15 - k2, true, partner);
-    const cf2 w = tw2[k2 * 16 + k1];  // W512^(k1 + 16 k2)
+    const cf2 w = tw2(K);  // W512^(k1 + 16 k2)
     float plo, phi;
     split_pair(xr[k2], xi[k2], br, bi, w.x, w.y, plo, phi);
     const int lo = k1 + 16 * k2;
@@ -237,6 +243,14 @@ VADB_HD void fft_split_store(const float (&xr)[16], const float (&xi)[16], int k
     if (k2 != 0 || k1 != 0) store(256 - lo, phi);
   });
   if (k1 == 0) store(128, 4.0f * fmaf(xr[8], xr[8], xi[8] * xi[8]));
+}
+#if defined(__CUDACC__)
+#pragma nv_exec_check_disable
+#endif
+template <class XCH, class STORE>
+VADB_HD void fft_split_store(const float (&xr)[16], const float (&xi)[16], int k1, const cf2* tw2,
+                             XCH&& xch, STORE&& store) {
+  fft_split_store_tw(xr, xi, k1, [&](auto K) { return tw2[decltype(K)::value * 16 + k1]; }, xch, store);
 }
 
 // ---- mel + log: lane = frame; P points at column `lane` of the [256][pitch] power tile -------
@@ -255,12 +269,19 @@ VADB_HD void mel_group(const float* P, float* logE) {
   static_for<0, kMelGroupCount[G]>([&](auto J) {
     constexpr int m = kMelGroupFilter[G][J];
     constexpr int lo = kMelLo[m], hi = kMelHi[m], off = kMelOff[m];
-    float e0 = 0.0f, e1 = 0.0f;  // two chains: halves the dependent-FFMA latency
+    float e0 = 0.0f, e1 = 0.0f, e2 = 0.0f, e3 = 0.0f;  // four chains: dependent-FFMA latency / 4
     static_for<lo, hi>([&](auto K) {
       constexpr int k = K;
-      if constexpr (((k - lo) & 1) == 0) e0 = fmaf(P[k * PITCH], c_par.melw[off + k - lo], e0);
-      else e1 = fmaf(P[k * PITCH], c_par.melw[off + k - lo], e1);
+      constexpr int c = (k - lo) & 3;
+      const float pw = P[k * PITCH];
+      const float w = c_par.melw[off + k - lo];
+      if constexpr (c == 0) e0 = fmaf(pw, w, e0);
+      else if constexpr (c == 1) e1 = fmaf(pw, w, e1);
+      else if constexpr (c == 2) e2 = fmaf(pw, w, e2);
+      else e3 = fmaf(pw, w, e3);
     });
+    e0 = (e0 + e2) + (e1 + e3);
+    e1 = 0.0f;
     logE[m * OPITCH] = log2_energy(e0 + e1);
   });
 }
@@ -282,10 +303,45 @@ VADB_HD void mel_group_dispatch(int g, const float* P, float* logE) {
 // DCT-II(ortho)[:13] x lifter x log10(2) of the 26 log2-energies of one frame (column).
 template <int PITCH>
 VADB_HD float dct_coef(const float* logE, int c) {
-  float acc = 0.0f;
+  float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;  // four chains instead of one 26-long one
 #pragma unroll
-  for (int n = 0; n < kNMel; ++n) acc = fmaf(logE[n * PITCH], c_par.dct[c * kNMel + n], acc);
-  return acc;
+  for (int n = 0; n < 24; n += 4) {
+    a0 = fmaf(logE[(n + 0) * PITCH], c_par.dct[c * kNMel + n + 0], a0);
+    a1 = fmaf(logE[(n + 1) * PITCH], c_par.dct[c * kNMel + n + 1], a1);
+    a2 = fmaf(logE[(n + 2) * PITCH], c_par.dct[c * kNMel + n + 2], a2);
+    a3 = fmaf(logE[(n + 3) * PITCH], c_par.dct[c * kNMel + n + 3], a3);
+  }
+  a0 = fmaf(logE[24 * PITCH], c_par.dct[c * kNMel + 24], a0);
+  a1 = fmaf(logE[25 * PITCH], c_par.dct[c * kNMel + 25], a1);
+  return (a0 + a2) + (a1 + a3);
+}
+
+// Two coefficients of the same frame at once (shares the 26 loads, 8 independent chains).
+template <int PITCH>
+VADB_HD void dct_coef2(const float* logE, int ca, int cb, float& ra, float& rb) {
+  float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f, b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
+#pragma unroll
+  for (int n = 0; n < 24; n += 4) {
+    const float l0 = logE[(n + 0) * PITCH], l1 = logE[(n + 1) * PITCH], l2 = logE[(n + 2) * PITCH],
+                l3 = logE[(n + 3) * PITCH];
+    a0 = fmaf(l0, c_par.dct[ca * kNMel + n + 0], a0); b0 = fmaf(l0, c_par.dct[cb * kNMel + n + 0], b0);
+    a1 = fmaf(l1, c_par.dct[ca * kNMel + n + 1], a1); b1 = fmaf(l1, c_par.dct[cb * kNMel + n + 1], b1);
+    a2 = fmaf(l2, c_par.dct[ca * kNMel + n + 2], a2); b2 = fmaf(l2, c_par.dct[cb * kNMel + n + 2], b2);
+    a3 = fmaf(l3, c_par.dct[ca * kNMel + n + 3], a3); b3 = fmaf(l3, c_par.dct[cb * kNMel + n + 3], b3);
+  }
+  const float l24 = logE[24 * PITCH], l25 = logE[25 * PITCH];
+  a0 = fmaf(l24, c_par.dct[ca * kNMel + 24], a0); b0 = fmaf(l24, c_par.dct[cb * kNMel + 24], b0);
+  a1 = fmaf(l25, c_par.dct[ca * kNMel + 25], a1); b1 = fmaf(l25, c_par.dct[cb * kNMel + 25], b1);
+  ra = (a0 + a2) + (a1 + a3);
+  rb = (b0 + b2) + (b1 + b3);
+}
+
+VADB_HD float vadb_rsqrt(float v) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(v);  // MUFU.RSQ, <= 2 ulp
+#else
+  return 1.0f / sqrtf(v);
+#endif
 }
 
 // ---- 5-frame window features ------------------------------------------------------------------
@@ -304,7 +360,7 @@ VADB_HD bool window_features(const float (&r)[5][kNCep], int mode, float (&x)[kN
       const float var = fmaf(d4, d4, fmaf(d3, d3, fmaf(d2, d2, fmaf(d1, d1, d0 * d0)))) * 0.2f;
       // exact-arithmetic semantics of np.std == 0: all five equal -> 0/0 = nan
       const bool alleq = (c0 == c1) && (c1 == c2) && (c2 == c3) && (c3 == c4);
-      z = alleq ? NAN : d2 / sqrtf(var);
+      z = alleq ? NAN : d2 * vadb_rsqrt(var);
       ok = ok && (fabsf(z) <= 3.0e38f);  // false for nan and inf
     }
     x[k] = z;
@@ -332,7 +388,7 @@ VADB_HD bool window_features_range(const float* ring, int c, int mode, float (&o
       const float d0 = c0 - mu, d1 = c1 - mu, d2 = c2 - mu, d3 = c3 - mu, d4 = c4 - mu;
       const float var = fmaf(d4, d4, fmaf(d3, d3, fmaf(d2, d2, fmaf(d1, d1, d0 * d0)))) * 0.2f;
       const bool alleq = (c0 == c1) && (c1 == c2) && (c2 == c3) && (c3 == c4);
-      z = alleq ? NAN : d2 / sqrtf(var);
+      z = alleq ? NAN : d2 * vadb_rsqrt(var);
       ok = ok && (fabsf(z) <= 3.0e38f);
     }
     out[3 * (k - K0) + 0] = z;

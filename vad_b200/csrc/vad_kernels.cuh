@@ -237,6 +237,8 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
       for (int r = 0; r < 2; ++r) {
         const int fi = warp * 4 + r * 2 + h;
         const uint32_t* w32 = stage32 + fi * (kHop / 2);
+        // (keeping the 46 twiddle values in registers instead of re-reading the shared tables was
+        // measured neutral for the TC variant and spilled in the FP32-FFN variant: not used)
         warp_fft_pair<13>([&](float (&xr)[16], float (&xi)[16]) { fft_load_pcm(w32, t, xr, xi); }, ex, s_tw1,
                           s_tw2, s_P, fi, lane);
       }
@@ -257,8 +259,14 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
       // ---- DCT phase -> MFCC ring -----------------------------------------------------------
       {
         const int col = (s * kStepFrames + lane) % kRing;
-        s_ring[warp * kRing + col] = dct_coef<32>(s_logE + lane, warp);
-        if (warp + 8 < kNCep) s_ring[(warp + 8) * kRing + col] = dct_coef<32>(s_logE + lane, warp + 8);
+        if (warp + 8 < kNCep) {
+          float ra, rb;
+          dct_coef2<32>(s_logE + lane, warp, warp + 8, ra, rb);
+          s_ring[warp * kRing + col] = ra;
+          s_ring[(warp + 8) * kRing + col] = rb;
+        } else {
+          s_ring[warp * kRing + col] = dct_coef<32>(s_logE + lane, warp);
+        }
       }
 
       if (block_now) {
