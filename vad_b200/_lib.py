@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libvadb200.so")
+LIB_PATH = os.environ.get("VADB200_LIB") or os.path.join(HERE, "libvadb200.so")  # override: A/B experiments only
 
 
 class VadB200Error(RuntimeError):

@@ -8,18 +8,21 @@
 //
 // Precision: logits must stay within 1e-3 of the float64 oracle, so every operand is split into
 // two tf32 terms, x = x_hi + x_lo (x_hi = top 19 bits, x_lo = x - x_hi exactly), and each layer
-// issues three MMAs per k-step: a_hi.b_hi + a_lo.b_hi + a_hi.b_lo (the dropped lo.lo term is
-// <= 2^-20 relative).  Accumulation is fp32 in TMEM.
+// needs a_hi.b_hi + a_lo.b_hi + a_hi.b_lo (the dropped lo.lo term is <= 2^-20 relative), fp32
+// accumulation in TMEM.  clock64 stamps showed every one of these tiny K=8 MMAs costs ~85 cycles
+// whatever its N (latency-, not math-bound), so the B operand is stored as [B_hi | B_lo] (2N rows)
+// and each k-step issues TWO instructions instead of three:
+//     D'[0:2N] += a_hi . [B_hi | B_lo]      D'[0:N] += a_lo . B_hi
+// and the epilogue adds the two halves D'[c] + D'[N + c].
 //
 // One tile = 128 frames = 128 threads (4 warps; warp w owns TMEM lanes 32 (w % 4) ..+31, thread =
 // frame = lane).  TMEM map (256 columns per CTA, 2 CTAs per SM = all 512):
 //   [  0,128)  A operand of the current layer: hi in [0,K), lo in [K,2K)   (K = 48, 64, 32, 16)
-//   [128,192)  D1 (64)  -> later D3 [128,144) and D4 [144,160)
-//   [192,224)  D2 (32)
-// Weights (B operand, N x K, K-major, SWIZZLE_NONE canonical layout: 8x16B core matrices,
-// core (kc, nc) at (kc * N/8 + nc) * 128 B, so SBO = 128 B and LBO = N/8 * 128 B) are prepared
-// once on the host (hi block then lo block per layer) and arrive in shared memory by one TMA
-// bulk copy.
+//   [128,256)  D1' (2 x 64)  -> later D2' [128,192) (2 x 32)
+//   [192,224)  D3' (2 x 16)      [224,256)  D4' (2 x 16)
+// Weights (B operand, 2N x K, K-major, SWIZZLE_NONE canonical layout: 8x16B core matrices, core
+// (kc, nc) at (kc * 2N/8 + nc) * 128 B, rows [0,N) = hi, [N,2N) = lo, so SBO = 128 B and
+// LBO = 2N/8 * 128 B) are prepared once on the host and arrive in shared memory by one TMA bulk copy.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -43,13 +46,13 @@ constexpr int kTcK3 = 32, kTcN3 = 16;
 constexpr int kTcK4 = 16, kTcN4 = 16;   // 3 -> 16 (M = 128 needs N % 16 == 0)
 constexpr int kTcBlk1 = kTcK1 * kTcN1 * 4, kTcBlk2 = kTcK2 * kTcN2 * 4, kTcBlk3 = kTcK3 * kTcN3 * 4,
               kTcBlk4 = kTcK4 * kTcN4 * 4;
-constexpr int kTcOff1 = 0;
+constexpr int kTcOff1 = 0;  // each layer: one [kc][2N/8][8][4] block of 2 * kTcBlk bytes
 constexpr int kTcOff2 = kTcOff1 + 2 * kTcBlk1;
 constexpr int kTcOff3 = kTcOff2 + 2 * kTcBlk2;
 constexpr int kTcOff4 = kTcOff3 + 2 * kTcBlk3;
 constexpr int kTcBlobBytes = kTcOff4 + 2 * kTcBlk4;  // 47,104
 constexpr int kTmemCols = 256;
-constexpr int kTmA = 0, kTmD1 = 128, kTmD3 = 128, kTmD4 = 144, kTmD2 = 192;
+constexpr int kTmA = 0, kTmD1 = 128, kTmD2 = 128, kTmD3 = 192, kTmD4 = 224;
 
 // ---- host side: pack Keras (in,out) weights into the canonical hi/lo blob --------------------------
 inline float tf32_hi(float x) {
@@ -60,27 +63,25 @@ inline float tf32_hi(float x) {
   memcpy(&r, &u, 4);
   return r;
 }
-inline void tc_pack_layer(const float* W /*[k_real][n_real]*/, int k_real, int n_real, int K, int N, float* hi,
-                          float* lo, bool permute_features = false) {
-  for (int i = 0; i < K * N; ++i) hi[i] = lo[i] = 0.0f;
+inline void tc_pack_layer(const float* W /*[k_real][n_real]*/, int k_real, int n_real, int K, int N, float* blk,
+                          bool permute_features = false) {
+  for (int i = 0; i < 2 * K * N; ++i) blk[i] = 0.0f;
   for (int n = 0; n < n_real; ++n)
     for (int kk = 0; kk < k_real; ++kk) {
       const float w = W[kk * n_real + n];
       const int k = permute_features ? tc_feat_col(kk) : kk;
-      const int idx = ((k / 4) * (N / 8) + (n / 8)) * 32 + (n % 8) * 4 + (k % 4);
-      hi[idx] = tf32_hi(w);
-      lo[idx] = w - hi[idx];
+      const float hi = tf32_hi(w);
+      const int ihi = ((k / 4) * (2 * N / 8) + (n / 8)) * 32 + (n % 8) * 4 + (k % 4);
+      const int ilo = ((k / 4) * (2 * N / 8) + ((N + n) / 8)) * 32 + ((N + n) % 8) * 4 + (k % 4);
+      blk[ihi] = hi;
+      blk[ilo] = w - hi;
     }
 }
 inline void tc_pack_weights(const ConstParams& p, unsigned char* blob /*kTcBlobBytes*/) {
-  tc_pack_layer(p.W1, kNFeat, kH1, kTcK1, kTcN1, reinterpret_cast<float*>(blob + kTcOff1),
-                reinterpret_cast<float*>(blob + kTcOff1 + kTcBlk1), true);
-  tc_pack_layer(p.W2, kH1, kH2, kTcK2, kTcN2, reinterpret_cast<float*>(blob + kTcOff2),
-                reinterpret_cast<float*>(blob + kTcOff2 + kTcBlk2));
-  tc_pack_layer(p.W3, kH2, kH3, kTcK3, kTcN3, reinterpret_cast<float*>(blob + kTcOff3),
-                reinterpret_cast<float*>(blob + kTcOff3 + kTcBlk3));
-  tc_pack_layer(p.W4, kH3, kNCls, kTcK4, kTcN4, reinterpret_cast<float*>(blob + kTcOff4),
-                reinterpret_cast<float*>(blob + kTcOff4 + kTcBlk4));
+  tc_pack_layer(p.W1, kNFeat, kH1, kTcK1, kTcN1, reinterpret_cast<float*>(blob + kTcOff1), true);
+  tc_pack_layer(p.W2, kH1, kH2, kTcK2, kTcN2, reinterpret_cast<float*>(blob + kTcOff2));
+  tc_pack_layer(p.W3, kH2, kH3, kTcK3, kTcN3, reinterpret_cast<float*>(blob + kTcOff3));
+  tc_pack_layer(p.W4, kH3, kNCls, kTcK4, kTcN4, reinterpret_cast<float*>(blob + kTcOff4));
 }
 
 #if defined(__CUDACC__)
@@ -178,20 +179,18 @@ __host__ __device__ constexpr uint32_t tc_idesc(int n) {
          (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
 }
 
-// One layer: 3 MMAs per k-step (hi.hi, lo.hi, hi.lo); executed by ONE thread.
+// One layer: 2 MMAs per k-step (a_hi . [B_hi | B_lo] into 2N columns, a_lo . B_hi into the first N);
+// executed by ONE thread.
 template <int K, int N>
-__device__ __forceinline__ void tc_issue_layer(uint32_t tm_base, uint32_t d_col, uint32_t w_smem /*hi block*/,
-                                               uint64_t* done_bar) {
-  constexpr uint32_t lbo = (N / 8) * 128, sbo = 128, blk = K * N * 4;
-  constexpr uint32_t idesc = tc_idesc(N);
+__device__ __forceinline__ void tc_issue_layer(uint32_t tm_base, uint32_t d_col, uint32_t w_smem, uint64_t* done_bar) {
+  constexpr uint32_t lbo = (2 * N / 8) * 128, sbo = 128;
+  constexpr uint32_t idesc_2n = tc_idesc(2 * N), idesc_n = tc_idesc(N);
   const uint32_t a_hi = tm_base + kTmA, a_lo = tm_base + kTmA + K, d = tm_base + d_col;
 #pragma unroll
   for (int j = 0; j < K / 8; ++j) {
-    const uint64_t b_hi = tc_smem_desc(w_smem + 2 * j * lbo, lbo, sbo);
-    const uint64_t b_lo = tc_smem_desc(w_smem + blk + 2 * j * lbo, lbo, sbo);
-    umma_tf32_ts(d, a_lo + 8 * j, b_hi, idesc, j > 0 ? 1u : 0u);
-    umma_tf32_ts(d, a_hi + 8 * j, b_lo, idesc, 1u);
-    umma_tf32_ts(d, a_hi + 8 * j, b_hi, idesc, 1u);
+    const uint64_t b = tc_smem_desc(w_smem + 2 * j * lbo, lbo, sbo);
+    umma_tf32_ts(d, a_hi + 8 * j, b, idesc_2n, j > 0 ? 1u : 0u);
+    umma_tf32_ts(d, a_lo + 8 * j, b, idesc_n, 1u);
   }
   umma_commit(done_bar);
 }
@@ -211,13 +210,18 @@ __device__ __forceinline__ void tc_hidden_epilogue(uint32_t tl, uint32_t d_col, 
   const int base = hidx * W;
 #pragma unroll
   for (int c0 = 0; c0 < W; c0 += CH) {
-    uint32_t v[CH], hi[CH], lo[CH];
-    if constexpr (CH == 16) tmem_ld16(tl + d_col + base + c0, v);
-    else tmem_ld8(tl + d_col + base + c0, v);
+    uint32_t v[CH], u[CH], hi[CH], lo[CH];
+    if constexpr (CH == 16) {
+      tmem_ld16(tl + d_col + base + c0, v);           // a . B_hi
+      tmem_ld16(tl + d_col + NOUT + base + c0, u);    // a_hi . B_lo
+    } else {
+      tmem_ld8(tl + d_col + base + c0, v);
+      tmem_ld8(tl + d_col + NOUT + base + c0, u);
+    }
     tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < CH; ++i) {
-      const float a = fmaxf(__uint_as_float(v[i]) + bias[base + c0 + i], 0.0f);
+      const float a = fmaxf((__uint_as_float(v[i]) + __uint_as_float(u[i])) + bias[base + c0 + i], 0.0f);
       tc_split(a, hi[i], lo[i]);
     }
     if constexpr (CH == 16) {
@@ -259,52 +263,69 @@ __device__ __forceinline__ void tc_store_a1_half(uint32_t tl, int hidx, const fl
 // blob (already landed); mma_bar: mbarrier (count 1) whose current phase parity is `par` (4 phases).
 template <int HALVES>
 __device__ __forceinline__ uint32_t ffn_tc_tile(float (&logit)[kNCls], uint32_t tm_base, int wq, int hidx,
-                                                bool is_issuer, uint32_t w_smem, uint64_t* mma_bar, uint32_t par) {
+                                                bool is_issuer, uint32_t w_smem, uint64_t* mma_bar, uint32_t par,
+                                                long long* ts = nullptr, int dbg = 0) {
   const uint32_t tl = tm_base + (static_cast<uint32_t>(32 * wq) << 16);
+#define VADB_TS(i) do { if (ts) ts[i] = clock64(); } while (0)
   tmem_wait_st();
   tc_fence_before();
   tc_bar<HALVES>();
-  if (is_issuer) {
+  VADB_TS(3);
+  if (is_issuer && !(dbg & 32)) {
     tc_fence_after();
     tc_issue_layer<kTcK1, kTcN1>(tm_base, kTmD1, w_smem + kTcOff1, mma_bar);
   }
-  tc_mbar_wait(mma_bar, par); par ^= 1u;
+  VADB_TS(4);
+  if (!(dbg & 32)) { tc_mbar_wait(mma_bar, par); par ^= 1u; }
   tc_fence_after();
-  tc_hidden_epilogue<kTcN1, HALVES>(tl, kTmD1, c_par.b1, hidx);
+  VADB_TS(5);
+  if (!(dbg & 128)) tc_hidden_epilogue<kTcN1, HALVES>(tl, kTmD1, c_par.b1, hidx);
+  VADB_TS(6);
   tc_fence_before();
   tc_bar<HALVES>();
-  if (is_issuer) {
+  if (is_issuer && !(dbg & 32)) {
     tc_fence_after();
     tc_issue_layer<kTcK2, kTcN2>(tm_base, kTmD2, w_smem + kTcOff2, mma_bar);
   }
-  tc_mbar_wait(mma_bar, par); par ^= 1u;
+  VADB_TS(7);
+  if (!(dbg & 32)) { tc_mbar_wait(mma_bar, par); par ^= 1u; }
   tc_fence_after();
-  tc_hidden_epilogue<kTcN2, HALVES>(tl, kTmD2, c_par.b2, hidx);
+  VADB_TS(8);
+  if (!(dbg & 128)) tc_hidden_epilogue<kTcN2, HALVES>(tl, kTmD2, c_par.b2, hidx);
+  VADB_TS(9);
   tc_fence_before();
   tc_bar<HALVES>();
-  if (is_issuer) {
+  if (is_issuer && !(dbg & 32)) {
     tc_fence_after();
     tc_issue_layer<kTcK3, kTcN3>(tm_base, kTmD3, w_smem + kTcOff3, mma_bar);
   }
-  tc_mbar_wait(mma_bar, par); par ^= 1u;
+  VADB_TS(10);
+  if (!(dbg & 32)) { tc_mbar_wait(mma_bar, par); par ^= 1u; }
   tc_fence_after();
-  tc_hidden_epilogue<kTcN3, HALVES>(tl, kTmD3, c_par.b3, hidx);
+  VADB_TS(11);
+  if (!(dbg & 128)) tc_hidden_epilogue<kTcN3, HALVES>(tl, kTmD3, c_par.b3, hidx);
+  VADB_TS(12);
   tc_fence_before();
   tc_bar<HALVES>();
-  if (is_issuer) {
+  if (is_issuer && !(dbg & 32)) {
     tc_fence_after();
     tc_issue_layer<kTcK4, kTcN4>(tm_base, kTmD4, w_smem + kTcOff4, mma_bar);
   }
-  tc_mbar_wait(mma_bar, par); par ^= 1u;
+  VADB_TS(13);
+  if (!(dbg & 32)) { tc_mbar_wait(mma_bar, par); par ^= 1u; }
   tc_fence_after();
+  VADB_TS(14);
   if (hidx == 0) {
-    uint32_t v[8];
+    uint32_t v[8], u[8];
     tmem_ld8(tl + kTmD4, v);
+    tmem_ld8(tl + kTmD4 + kTcN4, u);
     tmem_wait_ld();
 #pragma unroll
-    for (int o = 0; o < kNCls; ++o) logit[o] = __uint_as_float(v[o]) + c_par.b4[o];
+    for (int o = 0; o < kNCls; ++o) logit[o] = (__uint_as_float(v[o]) + __uint_as_float(u[o])) + c_par.b4[o];
   }
   tc_fence_before();  // the next tile's tcgen05.st must not overtake these loads
+  VADB_TS(15);
+#undef VADB_TS
   return par;
 }
 #endif  // __CUDACC__

@@ -71,6 +71,8 @@ struct FusedParams {
   long long row_base;     // subtracted from Segment::out_start (chunked host runs)
   int feat_mode;
   const unsigned char* tc_blob;  // canonical hi/lo tf32 weight blob (ffn_tc.cuh), TC variant only
+  long long* dbg_ts;             // timing experiments only: clock64 stamps of CTA 0's block phases [n][16]
+  int debug_skip;                // timing experiments only (env VADB200_DEBUG_SKIP): 1 FFT, 2 mel, 4 DCT, 8 block phase
 };
 
 // ---- PTX wrappers: mbarrier + TMA bulk copy (UBLKCP) --------------------------------------------
@@ -187,6 +189,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
     fence_mbar_init();
   }
   uint32_t tm_base = 0, w_par = 0, mma_par = 0;
+  int dbg_n = 0;
   if (TC) {
     if (warp == 0) tmem_alloc(s_tmem, kTmemCols);
     tc_fence_before();
@@ -197,6 +200,9 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
 
   unsigned gstep = 0;  // loads issued so far by this CTA == steps started; buffer = gstep & 1
   Segment seg;
+
+  // (Staggering the block-phase schedule of the two CTAs sharing an SM -- per-SM arrival rank via
+  // %smid -- was tried against the lockstep hypothesis and measured neutral: 232.1 vs 231.1 ms.)
 
   auto issue_load = [&](int step, int buf) {
     const long long start = seg.pcm_start + static_cast<long long>(step) * (kStepFrames * kHop);
@@ -235,6 +241,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
       cf2* ex = s_exch + (warp * 2 + h) * kExchFrame;
 #pragma unroll 1
       for (int r = 0; r < 2; ++r) {
+        if (p.debug_skip & 1) break;
         const int fi = warp * 4 + r * 2 + h;
         const uint32_t* w32 = stage32 + fi * (kHop / 2);
         // (keeping the 46 twiddle values in registers instead of re-reading the shared tables was
@@ -245,19 +252,19 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
       __syncthreads();
 
       // ---- mel + log phase -----------------------------------------------------------------
-      mel_group_dispatch<kPPitch, 32>(warp, s_P + lane, s_logE + lane);
+      if (!(p.debug_skip & 2)) mel_group_dispatch<kPPitch, 32>(warp, s_P + lane, s_logE + lane);
       const int computed = min((s + 1) * kStepFrames, n);
-      const bool block_now = ((s + 1) % kBlk) == 0 || s == nsteps - 1;
+      const bool block_now = (((s + 1) % kBlk) == 0 || s == nsteps - 1) && !(p.debug_skip & 8);
       const bool tc_now = TC && block_now && (computed - 2 - out_done) > 0;  // block-uniform
       if (tc_now) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // exch/P generic accesses before the TMA overwrite
       __syncthreads();
-      if (tc_now && tid == 0) {  // exch + P are idle until the next FFT phase: land the weight blob during the DCT
+      if (tc_now && tid == 0 && !(p.debug_skip & 16)) {  // exch + P are idle until the next FFT phase: land the weight blob during the DCT
         mbar_arrive_expect_tx(&s_bar[2], kTcBlobBytes);
         bulk_g2s(smem + kOffExch, p.tc_blob, kTcBlobBytes, &s_bar[2]);
       }
 
       // ---- DCT phase -> MFCC ring -----------------------------------------------------------
-      {
+      if (!(p.debug_skip & 4)) {
         const int col = (s * kStepFrames + lane) % kRing;
         if (warp + 8 < kNCep) {
           float ra, rb;
@@ -318,15 +325,24 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
               // thread (warp % 4, lane) = frame = TMEM lane; the two threads sharing a frame (hidx = warp / 4)
               // build the features of cepstral coefficients 0-6 / 7-12 and split every layer's columns.
               const int fr = tid & 127, hidx = tid >> 7;
+              long long* ts = (p.dbg_ts && blockIdx.x == 0 && tid == 0 && dbg_n < 64) ? p.dbg_ts + 16 * dbg_n : nullptr;
+              if (ts) ts[0] = clock64();
               const bool valid = fr < n_valid;
               const int c = out_done + (valid ? fr : 0);
               const uint32_t tl = tm_base + (static_cast<uint32_t>(32 * (warp & 3)) << 16);
               float xl[24], logit[kNCls];
               // the half's validity flag travels through shared memory (logE is idle here): ReLU's fmaxf
               // swallows NaNs, so validity cannot be read back from the logits
-              const bool ok_half = (hidx == 0) ? window_features_range<0, 7, kRing, 24>(s_ring, c, p.feat_mode, xl)
-                                               : window_features_range<7, 13, kRing, 24>(s_ring, c, p.feat_mode, xl);
+              bool ok_half = true;
+              if (p.debug_skip & 64) {
+#pragma unroll
+                for (int i = 0; i < 24; ++i) xl[i] = 0.5f;
+              } else {
+                ok_half = (hidx == 0) ? window_features_range<0, 7, kRing, 24>(s_ring, c, p.feat_mode, xl)
+                                      : window_features_range<7, 13, kRing, 24>(s_ring, c, p.feat_mode, xl);
+              }
               s_logE[tid] = ok_half ? 1.0f : 0.0f;
+              if (ts) ts[1] = clock64();
               tc_store_a1_half(tl, hidx, xl);
               if (p.feats && valid) {
                 const long long row = seg.out_start - p.row_base + (c - 2);
@@ -335,8 +351,11 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
 #pragma unroll
                   for (int g = 0; g < 3; ++g) p.feats[row * kNFeat + g * kNCep + k0 + k] = xl[3 * k + g];
               }
-              mbar_wait(&s_bar[2], w_par);              // weight blob landed (issued before the DCT phase)
-              mma_par = ffn_tc_tile<2>(logit, tm_base, warp & 3, hidx, tid == 0, smem_u32(wdst), &s_bar[3], mma_par);
+              if (!(p.debug_skip & 16)) mbar_wait(&s_bar[2], w_par);  // weight blob landed (issued before the DCT phase)
+              if (ts) ts[2] = clock64();
+              mma_par = ffn_tc_tile<2>(logit, tm_base, warp & 3, hidx, tid == 0, smem_u32(wdst), &s_bar[3], mma_par, ts,
+                                       p.debug_skip);
+              ++dbg_n;
               if (valid && hidx == 0) {
                 const bool ok = s_logE[fr] != 0.0f && s_logE[128 + fr] != 0.0f;  // ordered by the tile's bar.syncs
                 uint8_t lab = decide(logit);
@@ -353,7 +372,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
                 }
               }
             }
-            w_par ^= 1u;
+            if (!(p.debug_skip & 16)) w_par ^= 1u;
             __syncthreads();  // MMAs done reading the blob before the next FFT phase rewrites exch / P
           }
           out_done = max(out_done, computed - 2);

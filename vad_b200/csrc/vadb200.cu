@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -42,6 +43,7 @@ int cuda_fail(cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return cuda_fail(e__, #expr); \
   } while (0)
 
+long long* g_dbg_ts = nullptr;  // timing experiments only (vadb200_debug_timestamps)
 constexpr int kNumSmFallback = 148;
 constexpr int kHostBufs = 3;
 
@@ -128,7 +130,9 @@ int launch_fused(vadb200_plan* p, FusedParams fp, int n_segs, cudaStream_t st) {
   rc = ensure_constants(h, st);
   if (rc) return rc;
   CU(cudaMemsetAsync(p->d_counter, 0, sizeof(int), st));
-  const int grid = std::min(n_segs, 2 * h->num_sms);
+  const char* gps = std::getenv("VADB200_CTAS_PER_SM");  // occupancy experiments only
+  const int per_sm = gps ? std::max(1, std::atoi(gps)) : 2;
+  const int grid = std::min(n_segs, per_sm * h->num_sms);
   switch (p->mode) {
     case VADB200_MODE_MFCC: fused_kernel<0, 0><<<grid, kThreads, kFusedSmemBytes, st>>>(fp); break;
     case VADB200_MODE_DATASET: fused_kernel<1, 0><<<grid, kThreads, kFusedSmemBytes, st>>>(fp); break;
@@ -150,6 +154,9 @@ FusedParams base_params(vadb200_plan* p) {
   fp.tw1 = p->h->d_tw;
   fp.tw2 = p->h->d_tw + 256;
   fp.tc_blob = p->h->d_tc_blob;
+  const char* dbg = std::getenv("VADB200_DEBUG_SKIP");  // timing experiments only; results are garbage
+  fp.debug_skip = dbg ? std::atoi(dbg) : 0;
+  fp.dbg_ts = g_dbg_ts;
   return fp;
 }
 
@@ -160,6 +167,9 @@ extern "C" {
 const char* vadb200_last_error(void) { return g_err.c_str(); }
 int vadb200_version(void) { return VADB200_VERSION; }
 int64_t vadb200_launch_count(void) { return g_launches.load(); }
+// Timing experiments only (not in the public header): device buffer of 64 x 16 clock64 stamps written by
+// CTA 0 during its first block phases; pass NULL to switch off.
+int vadb200_debug_timestamps(long long* d_buf) { g_dbg_ts = d_buf; return 0; }
 
 void vadb200_default_config(vadb200_config* c) {
   if (!c) return;
