@@ -34,6 +34,9 @@ UNIT = "audio-s/s"
 FLOP_PER_FRAME_FUSED = 24663   # FFT 11520 + power 768 + mel 888 + log 26 + DCT 676 + window 340 + FFN 10208 + 237
 BYTES_PER_FRAME_FUSED = 321    # 160 int16 in + 1 label out
 FP32_NOMINAL_TFLOPS = 74.4     # 148 SM x 128 lanes x 2 x 1.965 GHz (fallback denominator)
+# dram__bytes_read.sum + dram__bytes_write.sum of fused_kernel<2,1> from the committed `ncu --set full`
+# capture (profiles/r1d_fused_kernel_tc_ncu_raw.csv: 5.830 GB + 0.024 GB for 17.874 M frames)
+NCU_DRAM_BYTES_PER_FRAME = (5.830362e9 + 23.980544e6) / 17874000.0
 
 
 def parse_args():
@@ -301,7 +304,10 @@ def main():
     achieved = frames * FLOP_PER_FRAME_FUSED / kern_s / 1e12
     hbm_ach = frames * BYTES_PER_FRAME_FUSED / kern_s / 1e9
     roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "fused_kernel<2,%d> (MFCC+FFN VAD, FFN on %s)" % (
+                "traffic": frames * NCU_DRAM_BYTES_PER_FRAME if a.ffn_impl == "tc" else None,
+                "traffic_note": "bytes per launch = frames x 327.5 B/frame from the ncu capture in profiles/ "
+                                "(algorithmic 321 B/frame: no re-reads)",
+                "kernel": "fused_kernel<2,%d> (MFCC+FFN VAD, FFN on %s)" % (
                     1 if a.ffn_impl == "tc" else 0, "tcgen05 tf32x3" if a.ffn_impl == "tc" else "FP32 CUDA cores"), "launches_per_step": 1,
                 "algorithmic_flop_per_frame": FLOP_PER_FRAME_FUSED, "frames_per_launch": int(frames),
                 "peak_source": peak_src, "nominal_fp32_tflops": FP32_NOMINAL_TFLOPS,
