@@ -113,3 +113,78 @@ def test_synth_matches_itself_and_is_int16():
     assert a.dtype == np.int16 and np.array_equal(a[2048:], b)
     big = synth_utterance(1234, 5, 160000).astype(np.float64)
     assert 500 < big.std() < 5000 and np.abs(big).max() <= 32767
+
+
+def test_sph_reader_roundtrip(tmp_path):
+    from vad_b200.io import read_sph
+    data = (np.arange(-3000, 3000, 7)).astype(np.int16)
+    head = ("NIST_1A\n   1024\nsample_count -i %d\nsample_n_bytes -i 2\nchannel_count -i 1\n"
+            "sample_byte_format -s2 10\nsample_rate -i 16000\nsample_coding -s3 pcm\nend_head\n" % len(data)).encode()
+    path = tmp_path / "x.sph"
+    path.write_bytes(head + b" " * (1024 - len(head)) + data.astype(">i2").tobytes())
+    rate, got = read_sph(str(path))
+    assert rate == 16000 and np.array_equal(got, data)
+    (tmp_path / "bad.sph").write_bytes(b"RIFFxxxx")
+    with pytest.raises(ValueError):
+        read_sph(str(tmp_path / "bad.sph"))
+
+
+def test_shard_balanced_property():
+    from hypothesis import given, settings, strategies as st
+    from vad_b200 import shard
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.integers(min_value=0, max_value=500000), min_size=1, max_size=60),
+           st.integers(min_value=1, max_value=8))
+    def prop(lengths, world):
+        parts = shard.shard_balanced(lengths, world)
+        assert len(parts) == world
+        allidx = np.concatenate(parts) if parts else np.array([])
+        assert sorted(allidx.tolist()) == list(range(len(lengths)))
+        for p in parts:
+            assert list(p) == sorted(p)
+        cost = np.maximum((np.array(lengths) - 401) // 160 + 1, 0)
+        loads = np.array([cost[p].sum() for p in parts])
+        assert loads.max() - loads.min() <= max(int(cost.max()), 1)
+        lo_hi = [shard.shard_contiguous(len(lengths), r, world) for r in range(world)]
+        assert lo_hi[0][0] == 0 and lo_hi[-1][1] == len(lengths)
+        assert all(a[1] == b[0] for a, b in zip(lo_hi, lo_hi[1:]))
+
+    prop()
+
+
+def test_framing_rule_property():
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(min_value=0, max_value=2000000))
+    def prop(n):
+        t = rm.n_frames(n)
+        # reference loop (dataset/file_processing.py:99-101)
+        if n <= 5000:
+            k, off = 0, 0
+            while n - off > 400:
+                k += 1
+                off += 160
+            assert t == k
+        assert (t == 0) == (n <= 400)
+        if t:
+            assert 160 * (t - 1) + 400 < n <= 160 * t + 400
+        assert rm.n_outputs(n) == max(t - 5, 0)
+
+    prop()
+
+
+def test_csv_sink_layout(tmp_path):
+    import csv
+    from vad_b200 import batch
+    hdr = batch.create_table_header(13)
+    assert len(hdr) == 40 and hdr[0] == "MFCC Coef1" and hdr[13] == "First delta1" and hdr[26] == "Second delta1" \
+        and hdr[-1] == "voiced"
+    feats = [[(np.arange(13.0), np.arange(13.0) + 100, np.arange(13.0) + 200)] * 2]
+    with open(tmp_path / "f.csv", "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(hdr)
+        batch.write_features(w, feats, 1)
+    rows = list(csv.reader(open(tmp_path / "f.csv")))
+    assert len(rows) == 3 and len(rows[1]) == 40 and float(rows[1][13]) == 100.0 and float(rows[1][-1]) == 1.0

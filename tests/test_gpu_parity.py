@@ -386,3 +386,103 @@ def test_error_codes(env):
         plan.mfcc(torch.zeros(1000, dtype=torch.int16, device=h.device))                # wrong mode
     empty = runtime.Plan(h, np.array([], dtype=np.int64), np.array([], dtype=np.int64), runtime.MODE_VAD)
     assert empty.total_rows == 0
+
+
+# ---- drop-ins around the hot path -------------------------------------------------------------------
+def test_process_file_and_scale_features_dropins(env, utts, tmp_path):
+    from scipy.io import wavfile
+    from vad_b200 import batch, mfcc as vm
+
+    class Q(object):
+        def __init__(self):
+            self.v = 4
+
+        def get(self):
+            return self.v
+
+        def put(self, v):
+            self.v = v
+
+    fb = vm.get_mel_filterbanks(300, 8000, 512, 26, 16000)
+    files = []
+    for i, name in enumerate(("synth_ragged", "tone_noise")):
+        path = str(tmp_path / ("u%d.wav" % i))
+        wavfile.write(path, 16000, utts[name + "/pcm"])
+        q = Q()
+        feats = batch.process_file([path, 400, 160, 512, fb, 13, q, None])
+        assert q.v == 5
+        ref = utts[name + "/dataset_rows"]
+        got = np.array([np.concatenate(f) for f in feats])
+        assert got.shape == ref.shape and np.all(np.abs(got - ref) <= 3e-4 + 1e-4 * np.abs(ref))
+        files.append(feats)
+    with pytest.raises(ValueError):
+        batch.process_file(["x.mp3", 400, 160, 512, fb, 13, Q(), None])
+    with pytest.raises(NotImplementedError):
+        batch.process_file([str(tmp_path / "u0.wav"), 256, 160, 512, fb, 13, Q(), None])
+    groups = [np.array([np.concatenate(f) for f in ff]) for ff in files]
+    want, _ = rm.scale_features(groups)
+    out = batch.scale_features(files)
+    assert out is files
+    for ff, w in zip(files, want):
+        got = np.array([np.concatenate(f) for f in ff])
+        assert np.all(np.abs(got - w) <= 1e-9 + 1e-9 * np.abs(w))
+
+
+def test_stm_segments_gather(env, tmp_path):
+    from vad_b200 import batch
+    h, _ = env
+    pcm = synth_utterance(77, 2, 16000 * 6)
+    stm = tmp_path / "t.stm"
+    stm.write_text("a 1 spk 0.50 1.75 <o,f0,male> hello world\n"
+                   "a 1 spk 1.75 2.00 <o> ignore_time_segment_in_scoring\n"
+                   "short line\n"
+                   "a 1 spk 3.10 5.20 <o,f0,male> more words\n")
+    starts, ends = batch.parse_transcription(str(stm), 16000)
+    assert list(starts) == [8000, 49600] and list(ends) == [28000, 83200]
+    frames = batch.split_into_frames(pcm, 400, 160, str(stm), 16000)
+    glued = np.concatenate([pcm[8000:28000], pcm[49600:83200]])
+    assert len(frames) == rm.n_frames(len(glued)) and np.array_equal(frames[3], glued[480:880])
+    rows = batch.mfcc_batch([glued], deltas=True, handle=h)[0].cpu().numpy()
+    want = rm.dataset_features(rm.mfcc_utterance(glued))
+    assert np.all(np.abs(rows - want) <= 3e-4 + 1e-4 * np.abs(want))
+
+
+def test_two_handles_with_different_weights(env):
+    """Constant-bank ownership switches between handles (and FFN implementations) without mixing weights."""
+    import torch
+    from vad_b200 import batch, runtime
+    h, w = env
+    w2 = rm.glorot_ffn(123)
+    h2 = runtime.Handle(h.device.index, ffn_weights=w2)
+    h2.set_ffn_impl(h.ffn_impl)
+    utts_ = [synth_utterance(3, i, 16000 + 500 * i) for i in range(6)]
+    for _ in range(2):                                   # alternate owners twice
+        for hh, ww in ((h, w), (h2, w2)):
+            labels, logits = batch.vad_batch(utts_, handle=hh, want_logits=True)
+            for u, la, lo in zip(utts_, labels, logits):
+                check_vad(la.cpu().numpy(), lo.cpu().numpy(), u, ww)
+            x = np.random.default_rng(1).standard_normal((50, 39)).astype(np.float32)
+            ref, _ = rm.ffn_forward(x, ww)
+            got = hh.ffn_predict(x)[1].cpu().numpy()
+            assert np.all(np.abs(got - ref) <= LOGIT_ATOL + LOGIT_RTOL * np.abs(ref))
+    h2.close()
+
+
+def test_concurrent_streams_share_one_handle(env):
+    import torch
+    from vad_b200 import batch, runtime
+    h, w = env
+    n_utt, L = 64, 80000
+    off, ln, stride = batch.uniform_layout(n_utt, L)
+    pcm = h.synth_pcm(n_utt, L, seed=5, utt_stride=stride)
+    plans = [runtime.Plan(h, off, ln, runtime.MODE_VAD) for _ in range(3)]
+    base, _, _ = plans[0].vad(pcm)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(device=h.device) for _ in plans]
+    outs = []
+    for p, st in zip(plans, streams):
+        with torch.cuda.stream(st):
+            outs.append(p.vad(pcm)[0])
+    torch.cuda.synchronize()
+    for o in outs:
+        assert torch.equal(o, base)

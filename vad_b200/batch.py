@@ -157,3 +157,26 @@ def scale_features(features):
                 fr[g][:] = scaled[i, g]
             i += 1
     return features
+
+
+# ---- feature sink: the CSV row layout of dataset/file_processing.py:110-148 -------
+def create_table_header(mfcc_len):
+    """dataset/file_processing.py:110-127: 13 'MFCC Coef', 13 'First delta', 13 'Second delta', 'voiced'."""
+    header = ['MFCC Coef' + str(i + 1) for i in range(mfcc_len)]
+    header += ['First delta' + str(i + 1) for i in range(mfcc_len)]
+    header += ['Second delta' + str(i + 1) for i in range(mfcc_len)]
+    header.append('voiced')
+    return header
+
+
+def write_features(writer, features, label):
+    """dataset/file_processing.py:130-148: one CSV row per frame, 39 features then the class label."""
+    for file_features in features:
+        writer.writerows([np.concatenate((ff[0], ff[1], ff[2], [label])) for ff in file_features])
+
+
+def write_feature_rows(writer, rows, label):
+    """Same sink for the packed [n, 39] row tensors of ``mfcc_batch(deltas=True)``."""
+    arr = rows.detach().cpu().numpy() if torch.is_tensor(rows) else np.asarray(rows)
+    lab = np.full((arr.shape[0], 1), label, dtype=arr.dtype)
+    writer.writerows(np.concatenate([arr, lab], axis=1))
