@@ -486,3 +486,18 @@ def test_concurrent_streams_share_one_handle(env):
     torch.cuda.synchronize()
     for o in outs:
         assert torch.equal(o, base)
+
+
+def test_pure_c_consumer_of_the_abi(tmp_path):
+    """gcc-compiled C program linking libvadb200.so: the boundary works without Python or CUDA headers."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "c_abi_smoke")
+    subprocess.check_call(["gcc", "-O1", "-o", exe, os.path.join(root, "tests", "c_abi_smoke.c"),
+                           "-L" + os.path.join(root, "vad_b200"), "-lvadb200",
+                           "-Wl,-rpath," + os.path.join(root, "vad_b200")])
+    out = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert out.returncode == 0, (out.returncode, out.stderr)
+    rows, speech, checksum, diff, launches = out.stdout.split()
+    assert int(rows) == rm.n_outputs(48000) + rm.n_outputs(20001) and 0 <= int(speech) <= int(rows)
+    assert int(launches) >= 2
