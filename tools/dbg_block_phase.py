@@ -1,4 +1,5 @@
-"""Timing experiment: clock64() stamps of CTA 0's tensor-core block phases (not part of the product API)."""
+"""Timing experiment: clock64() stamps of CTA 0's tensor-core block phases (not part of the product API).
+Needs the hook build:  python -m vad_b200.build --debug-hooks && VADB200_LIB=$PWD/vad_b200/libvadb200_dbg.so python tools/dbg_block_phase.py"""
 import ctypes as C, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

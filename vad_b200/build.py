@@ -20,21 +20,30 @@ def is_stale():
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force=False, verbose=False):
-    """Compile csrc/*.cu into vad_b200/libvadb200.so (cross-compiles without a GPU)."""
-    if not force and not is_stale():
+LIB_DEBUG = os.path.join(HERE, "libvadb200_dbg.so")
+
+
+def build(force=False, verbose=False, debug_hooks=False):
+    """Compile csrc/*.cu into vad_b200/libvadb200.so (cross-compiles without a GPU).
+    debug_hooks=True builds vad_b200/libvadb200_dbg.so instead: the same kernels plus the
+    timing-experiment hooks (VADB200_DEBUG_SKIP phase ablation, VADB200_CTAS_PER_SM, clock64 stamps)
+    used by tools/dbg_block_phase.py; select it with VADB200_LIB.  The hooks cost ~1 %, so the product
+    library never contains them."""
+    out = LIB_DEBUG if debug_hooks else LIB
+    if not debug_hooks and not force and not is_stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     if not os.path.isfile(nvcc):
         nvcc = "nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    cmd = [nvcc] + NVCC_FLAGS + (["-DVADB_DEBUG_HOOKS"] if debug_hooks else []) + \
+        (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + SOURCES
     r = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or r.returncode != 0:
         sys.stderr.write(r.stdout)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed building libvadb200.so")
-    return LIB
+        raise RuntimeError("nvcc failed building " + os.path.basename(out))
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, debug_hooks="--debug-hooks" in sys.argv))

@@ -56,6 +56,14 @@ struct Segment {
   int pad;
 };
 
+// Timing-experiment hooks (phase ablation mask, clock64 stamps) are compiled in only with
+// -DVADB_DEBUG_HOOKS (tools/ab.sh builds); the product build has none of their branches.
+#if defined(VADB_DEBUG_HOOKS)
+#define VADB_DBG(p) ((p).debug_skip)
+#else
+#define VADB_DBG(p) 0
+#endif
+
 struct FusedParams {
   const int16_t* pcm;
   long long pcm_len;      // one past the last readable sample index (relative to pcm)
@@ -241,7 +249,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
       cf2* ex = s_exch + (warp * 2 + h) * kExchFrame;
 #pragma unroll 1
       for (int r = 0; r < 2; ++r) {
-        if (p.debug_skip & 1) break;
+        if (VADB_DBG(p) & 1) break;
         const int fi = warp * 4 + r * 2 + h;
         const uint32_t* w32 = stage32 + fi * (kHop / 2);
         // (keeping the 46 twiddle values in registers instead of re-reading the shared tables was
@@ -252,19 +260,19 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
       __syncthreads();
 
       // ---- mel + log phase -----------------------------------------------------------------
-      if (!(p.debug_skip & 2)) mel_group_dispatch<kPPitch, 32>(warp, s_P + lane, s_logE + lane);
+      if (!(VADB_DBG(p) & 2)) mel_group_dispatch<kPPitch, 32>(warp, s_P + lane, s_logE + lane);
       const int computed = min((s + 1) * kStepFrames, n);
-      const bool block_now = (((s + 1) % kBlk) == 0 || s == nsteps - 1) && !(p.debug_skip & 8);
+      const bool block_now = (((s + 1) % kBlk) == 0 || s == nsteps - 1) && !(VADB_DBG(p) & 8);
       const bool tc_now = TC && block_now && (computed - 2 - out_done) > 0;  // block-uniform
       if (tc_now) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // exch/P generic accesses before the TMA overwrite
       __syncthreads();
-      if (tc_now && tid == 0 && !(p.debug_skip & 16)) {  // exch + P are idle until the next FFT phase: land the weight blob during the DCT
+      if (tc_now && tid == 0 && !(VADB_DBG(p) & 16)) {  // exch + P are idle until the next FFT phase: land the weight blob during the DCT
         mbar_arrive_expect_tx(&s_bar[2], kTcBlobBytes);
         bulk_g2s(smem + kOffExch, p.tc_blob, kTcBlobBytes, &s_bar[2]);
       }
 
       // ---- DCT phase -> MFCC ring -----------------------------------------------------------
-      if (!(p.debug_skip & 4)) {
+      if (!(VADB_DBG(p) & 4)) {
         const int col = (s * kStepFrames + lane) % kRing;
         if (warp + 8 < kNCep) {
           float ra, rb;
@@ -325,7 +333,10 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
               // thread (warp % 4, lane) = frame = TMEM lane; the two threads sharing a frame (hidx = warp / 4)
               // build the features of cepstral coefficients 0-6 / 7-12 and split every layer's columns.
               const int fr = tid & 127, hidx = tid >> 7;
-              long long* ts = (p.dbg_ts && blockIdx.x == 0 && tid == 0 && dbg_n < 64) ? p.dbg_ts + 16 * dbg_n : nullptr;
+              long long* ts = nullptr;
+#if defined(VADB_DEBUG_HOOKS)
+              if (p.dbg_ts && blockIdx.x == 0 && tid == 0 && dbg_n < 64) ts = p.dbg_ts + 16 * dbg_n;
+#endif
               if (ts) ts[0] = clock64();
               const bool valid = fr < n_valid;
               const int c = out_done + (valid ? fr : 0);
@@ -334,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
               // the half's validity flag travels through shared memory (logE is idle here): ReLU's fmaxf
               // swallows NaNs, so validity cannot be read back from the logits
               bool ok_half = true;
-              if (p.debug_skip & 64) {
+              if (VADB_DBG(p) & 64) {
 #pragma unroll
                 for (int i = 0; i < 24; ++i) xl[i] = 0.5f;
               } else {
@@ -351,10 +362,10 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
 #pragma unroll
                   for (int g = 0; g < 3; ++g) p.feats[row * kNFeat + g * kNCep + k0 + k] = xl[3 * k + g];
               }
-              if (!(p.debug_skip & 16)) mbar_wait(&s_bar[2], w_par);  // weight blob landed (issued before the DCT phase)
+              if (!(VADB_DBG(p) & 16)) mbar_wait(&s_bar[2], w_par);  // weight blob landed (issued before the DCT phase)
               if (ts) ts[2] = clock64();
               mma_par = ffn_tc_tile<2>(logit, tm_base, warp & 3, hidx, tid == 0, smem_u32(wdst), &s_bar[3], mma_par, ts,
-                                       p.debug_skip);
+                                       VADB_DBG(p));
               ++dbg_n;
               if (valid && hidx == 0) {
                 const bool ok = s_logE[fr] != 0.0f && s_logE[128 + fr] != 0.0f;  // ordered by the tile's bar.syncs
@@ -372,7 +383,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
                 }
               }
             }
-            if (!(p.debug_skip & 16)) w_par ^= 1u;
+            if (!(VADB_DBG(p) & 16)) w_par ^= 1u;
             __syncthreads();  // MMAs done reading the blob before the next FFT phase rewrites exch / P
           }
           out_done = max(out_done, computed - 2);

@@ -130,8 +130,12 @@ int launch_fused(vadb200_plan* p, FusedParams fp, int n_segs, cudaStream_t st) {
   rc = ensure_constants(h, st);
   if (rc) return rc;
   CU(cudaMemsetAsync(p->d_counter, 0, sizeof(int), st));
+#if defined(VADB_DEBUG_HOOKS)
   const char* gps = std::getenv("VADB200_CTAS_PER_SM");  // occupancy experiments only
   const int per_sm = gps ? std::max(1, std::atoi(gps)) : 2;
+#else
+  const int per_sm = 2;
+#endif
   const int grid = std::min(n_segs, per_sm * h->num_sms);
   switch (p->mode) {
     case VADB200_MODE_MFCC: fused_kernel<0, 0><<<grid, kThreads, kFusedSmemBytes, st>>>(fp); break;
@@ -154,9 +158,14 @@ FusedParams base_params(vadb200_plan* p) {
   fp.tw1 = p->h->d_tw;
   fp.tw2 = p->h->d_tw + 256;
   fp.tc_blob = p->h->d_tc_blob;
+#if defined(VADB_DEBUG_HOOKS)
   const char* dbg = std::getenv("VADB200_DEBUG_SKIP");  // timing experiments only; results are garbage
   fp.debug_skip = dbg ? std::atoi(dbg) : 0;
   fp.dbg_ts = g_dbg_ts;
+#else
+  fp.debug_skip = 0;
+  fp.dbg_ts = nullptr;
+#endif
   return fp;
 }
 
