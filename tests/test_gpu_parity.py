@@ -501,3 +501,46 @@ def test_pure_c_consumer_of_the_abi(tmp_path):
     rows, speech, checksum, diff, launches = out.stdout.split()
     assert int(rows) == rm.n_outputs(48000) + rm.n_outputs(20001) and 0 <= int(speech) <= int(rows)
     assert int(launches) >= 2
+
+
+def test_outputs_stay_inside_their_buffers(env):
+    """compute-sanitizer is closed on this pool, so check bounds ourselves: every output mode on a
+    ragged batch writes only its own rows (guard bands before / after each buffer stay intact) and
+    every row is written (no sentinel survives)."""
+    import torch
+    from vad_b200 import batch, runtime
+    h, w = env
+    lens = [401, 16003, 0, 1041, 48017, 7777, 400, 32000, 561, 9999]
+    utts_ = [synth_utterance(13, i, n) for i, n in enumerate(lens)]
+    flat, off, ln = batch.pack_utterances(utts_)
+    pcm = flat.to(h.device)
+    G = 1024
+
+    def guarded(n, dtype, fill):
+        buf = torch.full((n + 2 * G,), fill, dtype=dtype, device=h.device)
+        return buf, buf[G:G + n]
+
+    def bands_intact(buf, n, fill):
+        return bool((buf[:G] == fill).all()) and bool((buf[G + n:] == fill).all())
+
+    for mode, width in ((runtime.MODE_MFCC, 13), (runtime.MODE_DATASET, 39)):
+        plan = runtime.Plan(h, off, ln, mode)
+        buf, view = guarded(plan.total_rows * width, torch.float32, -777.0)
+        plan.mfcc(pcm, out=view.view(plan.total_rows, width))
+        torch.cuda.synchronize()
+        assert bands_intact(buf, plan.total_rows * width, -777.0)
+        assert not bool((view == -777.0).any())
+    plan = runtime.Plan(h, off, ln, runtime.MODE_VAD)
+    n = plan.total_rows
+    assert n == sum(rm.n_outputs(x) for x in lens)
+    lbuf, lview = guarded(n, torch.uint8, 77)
+    gbuf, gview = guarded(n * 3, torch.float32, -777.0)
+    fbuf, fview = guarded(n * 39, torch.float32, -777.0)
+    from vad_b200._lib import check
+    import ctypes as C
+    check(h.lib.vadb200_vad_packed(plan._p, C.c_void_p(pcm.data_ptr()), pcm.numel(), C.c_void_p(lview.data_ptr()),
+                                   C.c_void_p(gview.data_ptr()), C.c_void_p(fview.data_ptr()), 0, h.stream))
+    torch.cuda.synchronize()
+    assert bands_intact(lbuf, n, 77) and bands_intact(gbuf, n * 3, -777.0) and bands_intact(fbuf, n * 39, -777.0)
+    assert bool((lview <= 1).all())
+    assert not bool((gview == -777.0).any()) and not bool((fview == -777.0).any())
