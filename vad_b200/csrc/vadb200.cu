@@ -683,6 +683,28 @@ int vadb200_stream_feed(vadb200_bank* b, const int16_t* d_chunks, uint8_t* d_lab
   return 0;
 }
 
+#if defined(VADB_DEBUG_HOOKS)
+// Occupancy experiment (hook build only, not in the public header): FFT phase alone at minb CTAs per SM.
+int vadb200_exp_fft(vadb200_plan* p, const int16_t* d_pcm, int64_t pcm_len, int minb, void* stream) {
+  vadb200_handle* h = p->h;
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  FusedParams fp = base_params(p);
+  fp.pcm = d_pcm; fp.pcm_len = pcm_len; fp.seg_begin = 0; fp.seg_end = static_cast<int>(p->segs.size());
+  CU(cudaMemsetAsync(p->d_counter, 0, sizeof(int), st));
+  const int grid = std::min<int>(fp.seg_end, minb * h->num_sms);
+#define VADB_EXP(M)                                                                                          \
+  {                                                                                                          \
+    CU(cudaFuncSetAttribute(exp_fft_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpSmemBytes)); \
+    exp_fft_kernel<M><<<grid, kThreads, kExpSmemBytes, st>>>(fp, h->d_sink);                                 \
+  }
+  if (minb == 1) VADB_EXP(1) else if (minb == 2) VADB_EXP(2) else if (minb == 3) VADB_EXP(3) else VADB_EXP(4)
+#undef VADB_EXP
+  CU(cudaGetLastError());
+  return 0;
+}
+#endif
+
 // ---- bench support -----------------------------------------------------------------------------------------
 int vadb200_synth_pcm(vadb200_handle* h, int16_t* d_out, int64_t n_utt, int64_t utt_samples, int64_t utt_stride,
                       uint32_t seed, int64_t first_utt, void* stream) {
