@@ -35,8 +35,8 @@ FLOP_PER_FRAME_FUSED = 24663   # FFT 11520 + power 768 + mel 888
 BYTES_PER_FRAME_FUSED = 321    # 160 int16 in + 1 label out
 FP32_NOMINAL_TFLOPS = 74.4     # 148 SM x 128 lanes x 2 x 1.965 GHz (fallback denominator)
 # dram__bytes_read.sum + dram__bytes_write.sum of fused_kernel<2,1> from the committed `ncu --set full`
-# capture (profiles/r1d_fused_kernel_tc_ncu_raw.csv: 5.830 GB + 0.024 GB for 17.874 M frames)
-NCU_DRAM_BYTES_PER_FRAME = (5.830362e9 + 23.980544e6) / 17874000.0
+# capture of the final build (profiles/r1e_fused_kernel_tc_ncu_raw.csv: 5.830 GB + 0.023 GB for 17.874 M frames)
+NCU_DRAM_BYTES_PER_FRAME = (5.830388e9 + 23.418880e6) / 17874000.0
 
 
 def parse_args():
