@@ -7,9 +7,14 @@
  *
  * Conventions: every function returns 0 on success or a negative VADB200_E_* code and never
  * throws or aborts; vadb200_last_error() gives a thread-local message.  A handle is bound to
- * one CUDA device and used by one host thread at a time.  "d_" pointers are device memory,
- * "h_" pointers host memory; the caller owns every buffer.  `stream` is a cudaStream_t
- * passed as void* (NULL = the legacy default stream); device-pointer calls only enqueue work.
+ * one CUDA device.  The library keeps NO per-handle state in device globals: FFN weights travel
+ * with every launch as kernel parameters, so different handles (= different classifiers, as one
+ * SKLearnAnalyzer owns one classifier, sklearn_analyser.py:21-35) may be driven from different
+ * host threads concurrently; one handle's setters (vadb200_set_*) must not race with its own
+ * launches.  "d_" pointers are device memory, "h_" pointers host memory; the caller owns every
+ * buffer.  `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream);
+ * device-pointer calls only enqueue work, never synchronise and can be captured in CUDA graphs.
+ * A plan may be in flight on up to 16 streams at once (each launch takes its own work counter).
  */
 #ifndef VADB200_H_
 #define VADB200_H_
@@ -20,7 +25,7 @@
 extern "C" {
 #endif
 
-#define VADB200_VERSION 100
+#define VADB200_VERSION 200
 
 #define VADB200_OK 0
 #define VADB200_E_INVALID (-1)      /* bad argument (null, negative, misaligned) */
@@ -96,6 +101,14 @@ int vadb200_plan_create(vadb200_handle* h, const int64_t* h_offsets, const int64
 int vadb200_plan_destroy(vadb200_plan* p);
 int64_t vadb200_plan_total_rows(const vadb200_plan* p);
 int vadb200_plan_row_offsets(const vadb200_plan* p, int64_t* h_out /* n_utt + 1 */);
+/* Work decomposition of a plan: utterances are cut into segments of at most
+ * vadb200_plan_segment_frames() consecutive frames (chosen from the batch size: >= 16 segments per
+ * persistent CTA, at most 2048 frames).  vadb200_set_plan_segment_frames() overrides the choice
+ * for plans created afterwards (0 = automatic; else a multiple of 32 in [64, 2048]); results do
+ * not depend on it (tests use it to pin the benchmark's one-segment-per-utterance layout). */
+int64_t vadb200_plan_segment_frames(const vadb200_plan* p);
+int64_t vadb200_plan_segment_count(const vadb200_plan* p);
+int vadb200_set_plan_segment_frames(vadb200_handle* h, int frames);
 
 /* mfcc.get_mfcc over every frame (MODE_MFCC: d_out [rows][13]) or process_file's rows
  * (MODE_DATASET: d_out [rows][39]).  d_pcm must be 16-byte aligned; pcm_len = samples. */
@@ -115,6 +128,25 @@ int vadb200_vad_packed(vadb200_plan* p, const int16_t* d_pcm, int64_t pcm_len, u
 int vadb200_vad_host(vadb200_plan* p, const int16_t* h_pcm, int64_t pcm_len, uint8_t* h_labels,
                      float* h_logits /* nullable */, int feat_mode);
 int vadb200_set_host_chunk_samples(vadb200_handle* h, int64_t samples);
+/* The same host-buffer pipeline for MODE_MFCC / MODE_DATASET plans: h_out [rows][13 | 39] float32.
+ * Replaces the Pool.map(process_file) step of dataset_creator.process_files
+ * (dataset_creator.py:61-65) for a packed batch of decoded files. */
+int vadb200_mfcc_host(vadb200_plan* p, const int16_t* h_pcm, int64_t pcm_len, float* h_out);
+
+/* ---- feature sink and ingest (the steps either side of the path in the offline flow) --------
+ * dataset/utils.py:5-32 scale_features on packed dataset rows d_rows [n_rows][39], in place:
+ * one scalar mean and one population std per group {mfcc, d1, d2} over all n_rows x 13 values,
+ * accumulated in float64.  h_stats (nullable) receives {mean_mfcc, mean_d1, mean_d2, std_mfcc,
+ * std_d1, std_d2}; when given, the call synchronises `stream`. */
+int vadb200_scale_rows(vadb200_handle* h, float* d_rows, int64_t n_rows, double* h_stats, void* stream);
+/* Decode + gather 16-bit PCM on the device: segment i copies d_len[i] samples starting at sample
+ * index d_src_start[i] of the raw byte stream d_raw (2-byte aligned; big_endian != 0 swaps bytes:
+ * NIST SPHERE, dataset/sph.py:33-63) to d_dst[d_dst_start[i] ...].  With the .stm segment bounds
+ * of dataset/stm_parser.py:5-26 as (start, len) this is split_into_frames' concatenation
+ * (dataset/file_processing.py:87-94).  max_len = the largest d_len (host copy, sizes the grid). */
+int vadb200_ingest_pcm(vadb200_handle* h, const void* d_raw, int big_endian, const int64_t* d_src_start,
+                       const int64_t* d_dst_start, const int64_t* d_len, int n_seg, int64_t max_len,
+                       int16_t* d_dst, void* stream);
 
 /* ---- per-frame API (mfcc.py:59-78 as the reference calls it: one float frame at a time;
  * batched here over n explicit frames of frame_len <= 512 float32 samples) ------------------ */
@@ -142,7 +174,8 @@ int vadb200_lifter(vadb200_handle* h, const float* d_in, int64_t n_rows, int nco
                    float* d_out, void* stream);
 
 /* ---- streaming (SKLearnAnalyzer.feed_frame, sklearn_analyser.py:46-82, for many streams) ---
- * Each stream owns a 240-sample history and a 5-row MFCC ring on the device.  One feed =
+ * Each stream owns a 320-sample history (two hops; a frame = history + 80 new samples) and a
+ * 5-row MFCC ring on the device.  One feed =
  * one 160-sample (10 ms) chunk per stream; labels_out[i] is the decision for the frame fed
  * 3 frames earlier, or 255 while the ring is filling. */
 int vadb200_stream_bank_create(vadb200_handle* h, int n_streams, vadb200_bank** out);

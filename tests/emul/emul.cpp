@@ -23,39 +23,48 @@ constexpr int kPPitch = 34;
 constexpr int kStageSamples = (kStepFrames - 1) * kHop + kFrame;  // 5360
 
 cf2 g_tw1[256], g_tw2[128];
+FfnParams g_ffn;
 bool g_init = false;
 
 struct FrameThreads {  // registers of the 16 threads of one frame
   float xr[16][16], xi[16][16];
 };
+struct PairThreads {   // registers of the 16 threads of one half-warp: two frames per thread (f2 lanes)
+  f2 xr[16][16], xi[16][16];
+};
 
-void fft_frame_pcm(const uint32_t* w32, float* Pcol /* stride kPPitch */) {
-  FrameThreads th;
-  std::vector<cf2> ex(kExchFrame);
+// The fused kernel's warp_fft_quad for one half-warp: frame A at w32a, frame B `delta` words later;
+// powers go to P columns col, col + 1.
+void fft_pair_pcm(const uint32_t* w32a, int delta, float* P, int col) {
+  PairThreads th;
+  std::vector<f2> ex(kExchFrame);
   for (int t = 0; t < 16; ++t) {
-    fft_load_pcm(w32, t, th.xr[t], th.xi[t]);
+    fft_load_pcm2(w32a, delta, t, th.xr[t], th.xi[t]);
     fft_pass1<13>(th.xr[t], th.xi[t], g_tw1, t);
-    exch_store(ex.data(), t, th.xr[t], th.xi[t]);
   }
-  for (int k1 = 0; k1 < 16; ++k1) {
-    exch_load(ex.data(), k1, th.xr[k1], th.xi[k1]);
-    dft16<16>(th.xr[k1], th.xi[k1]);
-  }
+  for (int t = 0; t < 16; ++t) exch_store_plane(ex.data(), t, th.xr[t]);
+  for (int k1 = 0; k1 < 16; ++k1) exch_load_plane(ex.data(), k1, th.xr[k1]);
+  for (int t = 0; t < 16; ++t) exch_store_plane(ex.data(), t, th.xi[t]);
+  for (int k1 = 0; k1 < 16; ++k1) exch_load_plane(ex.data(), k1, th.xi[k1]);
+  for (int k1 = 0; k1 < 16; ++k1) dft16<16>(th.xr[k1], th.xi[k1]);
   // partner exchange: build everyone's send registers first (what __shfl_sync would read)
-  float sr[16][16], si[16][16];
+  static f2 sr[16][16], si[16][16];
   for (int k1 = 0; k1 < 16; ++k1)
     for (int j = 8; j < 16; ++j) {
       sr[k1][j] = (k1 == 0) ? th.xr[k1][(j + 1) & 15] : th.xr[k1][j];
       si[k1][j] = (k1 == 0) ? th.xi[k1][(j + 1) & 15] : th.xi[k1][j];
     }
   for (int k1 = 0; k1 < 16; ++k1) {
-    auto xch = [&](float /*mine*/, int j, bool imag, int partner) {
-      return imag ? si[partner][j] : sr[partner][j];
+    auto xch = [&](f2 /*mine*/, int j, bool imag, int partner) { return imag ? si[partner][j] : sr[partner][j]; };
+    auto store = [&](int bin, f2 v) {
+      P[bin * kPPitch + col] = v.x;
+      P[bin * kPPitch + col + 1] = v.y;
     };
-    auto store = [&](int bin, float v) { Pcol[bin * kPPitch] = v; };
     fft_split_store(th.xr[k1], th.xi[k1], k1, g_tw2, xch, store);
   }
 }
+
+inline int slot_of_col(int c) { return (c & ~3) | ((c >> 1) & 1) | ((c & 1) << 1); }
 
 void fft_frame_f32(const float* fr, int frame_len, float* Pcol) {
   FrameThreads th;
@@ -91,10 +100,10 @@ int emul_init(const float* ffn_weights) {
   MfccConfig cfg;
   std::vector<double> fb = mel_filterbank(cfg);
   std::string why;
-  if (!pack_mel_weights(fb.data(), c_par.melw, &why)) return -1;
-  folded_dct(cfg, c_par.dct);
+  if (!pack_mel_weights(fb.data(), c_tab.melw, &why)) return -1;
+  folded_dct(cfg, c_tab.dct);
   fft_twiddles(g_tw1, g_tw2);
-  float* dst = c_par.W1;
+  float* dst = g_ffn.W1;
   const size_t n = kNFeat * kH1 + kH1 + kH1 * kH2 + kH2 + kH2 * kH3 + kH3 + kH3 * kNCls + kNCls;
   if (ffn_weights) std::memcpy(dst, ffn_weights, n * sizeof(float));
   else std::memset(dst, 0, n * sizeof(float));
@@ -133,19 +142,20 @@ int emul_utterance(const int16_t* pcm, long long n_samples, int feat_mode, float
     const long long avail = std::min<long long>(n_samples - start, kStageSamples);
     std::memset(stage.data(), 0x55, stage.size() * sizeof(int16_t));  // stale garbage beyond the buffer
     std::memcpy(stage.data(), pcm + start, static_cast<size_t>(avail) * sizeof(int16_t));
-    // FFT phase: warp w, round r, half h -> frame slot fi = 4w + 2r + h
-    for (int fi = 0; fi < kStepFrames; ++fi) {
-      const uint32_t* w32 = reinterpret_cast<const uint32_t*>(stage.data()) + fi * (kHop / 2);
-      fft_frame_pcm(w32, P.data() + fi);
-    }
-    // mel + log phase: warp g = filter group, lane = frame slot
+    // FFT phase: warp w, half-warp h -> frame slots 4w + h and 4w + h + 2, P columns 4w + 2h, + 1
+    for (int w = 0; w < 8; ++w)
+      for (int h = 0; h < 2; ++h) {
+        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(stage.data()) + (4 * w + h) * (kHop / 2);
+        fft_pair_pcm(w32, kHop, P.data(), 4 * w + 2 * h);
+      }
+    // mel + log phase: warp g = filter group, lane = P column
     for (int g = 0; g < 8; ++g)
       for (int lane = 0; lane < 32; ++lane)
         mel_group_dispatch<kPPitch, 32>(g, P.data() + lane, logE.data() + lane);
     // DCT phase: warp w -> coefficients w and w + 8
     for (int c = 0; c < kNCep; ++c)
       for (int lane = 0; lane < 32; ++lane) {
-        const int f = s * kStepFrames + lane;
+        const int f = s * kStepFrames + slot_of_col(lane);
         ring[c * kRing + f % kRing] = dct_coef<32>(logE.data() + lane, c);
       }
     const int computed = std::min((s + 1) * kStepFrames, n);
@@ -163,7 +173,7 @@ int emul_utterance(const int16_t* pcm, long long n_samples, int feat_mode, float
         float x[kNFeat];
         const bool ok = window_features(r, feat_mode, x);
         float logit[kNCls];
-        ffn_forward(x, logit);
+        ffn_forward(g_ffn, x, logit);
         uint8_t lab = decide(logit);
         if (!ok) { logit[0] = logit[1] = logit[2] = NAN; lab = 0; }
         const size_t row = static_cast<size_t>(c - 2);

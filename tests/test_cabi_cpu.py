@@ -82,10 +82,6 @@ def test_product_never_imports_oracle():
 
 def test_mfcc_table_constructors_match_reference_golden(golden_dir):
     # host-side init tables of the drop-in module (no GPU needed)
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("vb_mfcc_host", os.path.join(ROOT, "vad_b200", "mfcc.py"),
-                                                  submodule_search_locations=None)
-    # import through the package so relative imports resolve
     from vad_b200 import mfcc as vm
     kat = np.load(os.path.join(golden_dir, "kat_frame.npz"))
     np.testing.assert_array_equal(np.array(vm.mel_from_hz(300, 8000, 26)), kat["mel_points"])

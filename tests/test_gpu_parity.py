@@ -14,8 +14,9 @@ from vad_b200.synth import synth_utterance
 
 pytestmark = pytest.mark.gpu
 
-MFCC_ATOL, MFCC_RTOL = 1e-4, 1e-4
-LOGIT_ATOL, LOGIT_RTOL = 1e-3, 1e-3
+from _parity import (MFCC_ATOL, MFCC_RTOL, LOGIT_ATOL, LOGIT_RTOL, ROW_ATOL, ROW_RTOL, mfcc_close, rows_close,
+                     check_vad)
+
 CASES = ["synth_1p5s", "synth_ragged", "exact_fit", "too_short", "silence_dc", "tone_noise"]
 
 
@@ -28,8 +29,8 @@ def env(request):
     w = rm.glorot_ffn(0)
     h = runtime.default_handle()
     h.set_ffn_weights(w)
-    assert h.ffn_impl == 1 or request.param == "fp32" or True
     h.set_ffn_impl(request.param)
+    assert h.ffn_impl == {"fp32": 0, "tc": 1}[request.param]
     yield h, w
     h.set_ffn_impl("tc")
 
@@ -37,25 +38,6 @@ def env(request):
 @pytest.fixture(scope="module")
 def utts(golden_dir):
     return np.load(os.path.join(golden_dir, "utterances.npz"))
-
-
-def mfcc_close(a, ref):
-    return np.all(np.abs(a - ref) <= MFCC_ATOL + MFCC_RTOL * np.abs(ref))
-
-
-def check_vad(labels, logits, pcm, w):
-    c, feats, ref_logits, ref_labels = rm.vad_utterance(pcm, w)
-    assert labels.shape == ref_labels.shape and logits.shape == ref_logits.shape
-    if ref_labels.shape[0] == 0:
-        return
-    fin = np.isfinite(feats).all(axis=1)
-    assert np.array_equal(np.isfinite(logits).all(axis=1), fin)
-    assert np.all(labels[~fin] == 0)
-    err = np.abs(logits[fin] - ref_logits[fin])
-    assert np.all(err <= LOGIT_ATOL + LOGIT_RTOL * np.abs(ref_logits[fin])), err.max()
-    srt = np.sort(ref_logits[fin], axis=1)
-    decisive = (srt[:, -1] - srt[:, -2]) > 2 * (LOGIT_ATOL + LOGIT_RTOL * np.abs(srt[:, -1]))
-    assert np.array_equal(labels[fin][decisive], ref_labels[fin][decisive])
 
 
 # ---- per-frame drop-in API (mfcc.py) ---------------------------------------------------------
@@ -102,7 +84,7 @@ def test_golden_utterances_all_modes(env, utts, name):
     ds = batch.mfcc_batch([pcm], deltas=True, handle=h)[0].cpu().numpy()
     ref_ds = utts[name + "/dataset_rows"]
     assert ds.shape == ref_ds.shape
-    assert np.all(np.abs(ds - ref_ds) <= 3e-4 + 1e-4 * np.abs(ref_ds))
+    assert rows_close(ds, ref_ds)
     labels, logits = batch.vad_batch([pcm], handle=h, want_logits=True)
     check_vad(labels[0].cpu().numpy(), logits[0].cpu().numpy(), pcm, w)
 
@@ -413,7 +395,7 @@ def test_process_file_and_scale_features_dropins(env, utts, tmp_path):
         assert q.v == 5
         ref = utts[name + "/dataset_rows"]
         got = np.array([np.concatenate(f) for f in feats])
-        assert got.shape == ref.shape and np.all(np.abs(got - ref) <= 3e-4 + 1e-4 * np.abs(ref))
+        assert got.shape == ref.shape and rows_close(got, ref)
         files.append(feats)
     with pytest.raises(ValueError):
         batch.process_file(["x.mp3", 400, 160, 512, fb, 13, Q(), None])
@@ -444,7 +426,7 @@ def test_stm_segments_gather(env, tmp_path):
     assert len(frames) == rm.n_frames(len(glued)) and np.array_equal(frames[3], glued[480:880])
     rows = batch.mfcc_batch([glued], deltas=True, handle=h)[0].cpu().numpy()
     want = rm.dataset_features(rm.mfcc_utterance(glued))
-    assert np.all(np.abs(rows - want) <= 3e-4 + 1e-4 * np.abs(want))
+    assert rows_close(rows, want)
 
 
 def test_two_handles_with_different_weights(env):

@@ -39,6 +39,12 @@ SIGNATURES = {
     "vadb200_plan_destroy": (C.c_int, [_P]),
     "vadb200_plan_total_rows": (_I64, [_P]),
     "vadb200_plan_row_offsets": (C.c_int, [_P, _P]),
+    "vadb200_plan_segment_frames": (_I64, [_P]),
+    "vadb200_plan_segment_count": (_I64, [_P]),
+    "vadb200_set_plan_segment_frames": (C.c_int, [_P, C.c_int]),
+    "vadb200_mfcc_host": (C.c_int, [_P, _P, _I64, _P]),
+    "vadb200_scale_rows": (C.c_int, [_P, _P, _I64, _P, _P]),
+    "vadb200_ingest_pcm": (C.c_int, [_P, _P, C.c_int, _P, _P, _P, C.c_int, _I64, _P, _P]),
     "vadb200_mfcc_packed": (C.c_int, [_P, _P, _I64, _P, _P]),
     "vadb200_vad_packed": (C.c_int, [_P, _P, _I64, _P, _P, _P, C.c_int, _P]),
     "vadb200_vad_host": (C.c_int, [_P, _P, _I64, _P, _P, C.c_int]),

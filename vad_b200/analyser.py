@@ -12,6 +12,20 @@ from . import runtime
 from .runtime import FEAT_ANALYSER
 
 
+def _handle_for(weights, handle):
+    """One analyser == one classifier (sklearn_analyser.py:21-35): weights given without an explicit
+    handle get a PRIVATE handle, so constructing a second object can never replace the classifier of
+    an earlier one.  The process-wide default handle serves only the weight-free mfcc.* functions and
+    objects that ask for it explicitly."""
+    if weights is None:
+        return handle or runtime.default_handle()
+    w = runtime.load_ffn_npz(weights) if isinstance(weights, str) else weights
+    if handle is None:
+        return runtime.Handle(ffn_weights=w)
+    handle.set_ffn_weights(w)      # explicit handle: the caller owns it and asked for this
+    return handle
+
+
 class Analyser:
     """realtime_analysis/analyser.py:4-15 (the reference's plugin boundary)."""
 
@@ -32,9 +46,7 @@ class FFNClassifier(object):
     (1 = VOICED, config.py:46; the FFN's music class 2 maps to 0), evaluated on the GPU."""
 
     def __init__(self, weights=None, handle=None):
-        self.handle = handle or runtime.default_handle()
-        if weights is not None:
-            self.handle.set_ffn_weights(runtime.load_ffn_npz(weights) if isinstance(weights, str) else weights)
+        self.handle = _handle_for(weights, handle)
         if not self.handle.has_ffn:
             raise RuntimeError("FFNClassifier needs FFN weights")
 
@@ -69,16 +81,13 @@ class FusedAnalyser(Analyser):
             raise NotImplementedError("vad_b200 kernels are compiled for the reference configuration only")
         self.sample_rate, self.fft_n, self.mfcc_num = sample_rate, int(fft_n), mfcc_num
         self.low_hz, self.high_hz, self.fbank_num = low_hz, high_hz, fbank_num
-        self.handle = handle or runtime.default_handle()
-        self.filterbank = self.handle.filterbank()
         if isinstance(classifier, str):
             with open(classifier, "rb") as f:
                 classifier = pickle.load(f)
         self.classifier = classifier
+        self.handle = _handle_for(ffn_weights if classifier is None else None, handle)
+        self.filterbank = self.handle.filterbank()
         if classifier is None:
-            if ffn_weights is not None:
-                self.handle.set_ffn_weights(
-                    runtime.load_ffn_npz(ffn_weights) if isinstance(ffn_weights, str) else ffn_weights)
             if not self.handle.has_ffn:
                 raise RuntimeError("FusedAnalyser needs FFN weights or an external classifier")
         self.frames_buffer = []
@@ -127,15 +136,13 @@ class StreamBank(object):
     frames earlier (the reference's feed_frame timing), or 255 while a stream's ring is filling.
     Chunk j completes frame j-2 (= 400 samples ending 80 samples into chunk j).  Per-stream state
     (320-sample history, 5-row MFCC ring) lives on the device; chunk input and label output go
-    through pinned host buffers."""
+    through pinned host buffers.  A tick (H2D of the chunks, the feed kernel, D2H of the labels)
+    is captured once into a CUDA graph and replayed: one graph launch per tick."""
 
     NOT_READY = 255
 
-    def __init__(self, n_streams, ffn_weights=None, handle=None):
-        self.handle = handle or runtime.default_handle()
-        if ffn_weights is not None:
-            self.handle.set_ffn_weights(
-                runtime.load_ffn_npz(ffn_weights) if isinstance(ffn_weights, str) else ffn_weights)
+    def __init__(self, n_streams, ffn_weights=None, handle=None, use_graph=True):
+        self.handle = _handle_for(ffn_weights, handle)
         if not self.handle.has_ffn:
             raise RuntimeError("StreamBank needs FFN weights")
         self.n = int(n_streams)
@@ -148,7 +155,8 @@ class StreamBank(object):
         self.d_labels = torch.zeros((self.n,), dtype=torch.uint8, device=dev)
         self.d_logits = torch.zeros((self.n, 3), dtype=torch.float32, device=dev)
         self.stream = torch.cuda.Stream(device=dev)
-        self._graph = None
+        self.use_graph = bool(use_graph)
+        self._graphs = {}
 
     def reset(self):
         self.bank.reset()
@@ -162,23 +170,35 @@ class StreamBank(object):
         if want_logits:
             self.h_logits.copy_(self.d_logits, non_blocking=True)
 
+    def _tick(self, want_logits):
+        """One H2D + kernel + D2H on ``self.stream``; returns after the labels are on the host."""
+        if self.use_graph:
+            g = self._graphs.get(want_logits)
+            if g is None:  # capture once (capturing does not execute: no chunk is consumed)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=self.stream):
+                    self._enqueue(want_logits)
+                self._graphs[want_logits] = g
+            with torch.cuda.stream(self.stream):
+                g.replay()
+        else:
+            with torch.cuda.stream(self.stream):
+                self._enqueue(want_logits)
+        self.stream.synchronize()
+
     def feed(self, chunks, want_logits=False):
         """chunks: array-like int16 [n, 160] on the host.  Blocks until labels are on the host."""
         src = torch.as_tensor(np.asarray(chunks, dtype=np.int16) if not torch.is_tensor(chunks) else chunks)
         if tuple(src.shape) != (self.n, 160):
             raise ValueError("chunks must have shape (%d, 160)" % self.n)
         self.h_chunks.copy_(src)
-        with torch.cuda.stream(self.stream):
-            self._enqueue(want_logits)
-        self.stream.synchronize()
+        self._tick(want_logits)
         if want_logits:
             return self.h_labels.numpy().copy(), self.h_logits.numpy().copy()
         return self.h_labels.numpy().copy()
 
     def feed_pinned(self):
-        """Low-latency tick: the caller has already written ``self.h_chunks`` (pinned); one
-        H2D + kernel + D2H is enqueued and awaited.  Returns a view of ``self.h_labels``."""
-        with torch.cuda.stream(self.stream):
-            self._enqueue(False)
-        self.stream.synchronize()
+        """Low-latency tick: the caller has already written ``self.h_chunks`` (pinned); one graph
+        launch (H2D + kernel + D2H) is issued and awaited.  Returns a view of ``self.h_labels``."""
+        self._tick(False)
         return self.h_labels

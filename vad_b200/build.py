@@ -7,8 +7,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvadb200.so")
 SOURCES = ["vadb200.cu"]
-DEPS = ["vadb200.cu", "vad_kernels.cuh", "vad_core.cuh", "vad_host_tables.h", "vad_tables.h",
-        os.path.join("..", "..", "include", "vadb200.h")]
+def _deps():
+    """Every source the library is compiled from: csrc/*.{cu,cuh,h} and the public header."""
+    names = [f for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
+    return names + [os.path.join("..", "..", "include", "vadb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-diag-suppress", "20091", "--shared", "-Xcompiler", "-fPIC"]
 
@@ -17,7 +19,7 @@ def is_stale():
     if not os.path.isfile(LIB):
         return True
     t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in _deps())
 
 
 LIB_DEBUG = os.path.join(HERE, "libvadb200_dbg.so")

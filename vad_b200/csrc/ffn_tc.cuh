@@ -77,7 +77,7 @@ inline void tc_pack_layer(const float* W /*[k_real][n_real]*/, int k_real, int n
       blk[ilo] = w - hi;
     }
 }
-inline void tc_pack_weights(const ConstParams& p, unsigned char* blob /*kTcBlobBytes*/) {
+inline void tc_pack_weights(const FfnParams& p, unsigned char* blob /*kTcBlobBytes*/) {
   tc_pack_layer(p.W1, kNFeat, kH1, kTcK1, kTcN1, reinterpret_cast<float*>(blob + kTcOff1), true);
   tc_pack_layer(p.W2, kH1, kH2, kTcK2, kTcN2, reinterpret_cast<float*>(blob + kTcOff2));
   tc_pack_layer(p.W3, kH2, kH3, kTcK3, kTcN3, reinterpret_cast<float*>(blob + kTcOff3));
@@ -262,7 +262,7 @@ __device__ __forceinline__ void tc_store_a1_half(uint32_t tl, int hidx, const fl
 // stored both halves.  Logits are returned to hidx == 0.  w_smem: shared-memory address of the weight
 // blob (already landed); mma_bar: mbarrier (count 1) whose current phase parity is `par` (4 phases).
 template <int HALVES>
-__device__ __forceinline__ uint32_t ffn_tc_tile(float (&logit)[kNCls], uint32_t tm_base, int wq, int hidx,
+__device__ __forceinline__ uint32_t ffn_tc_tile(const FfnBias& fb, float (&logit)[kNCls], uint32_t tm_base, int wq, int hidx,
                                                 bool is_issuer, uint32_t w_smem, uint64_t* mma_bar, uint32_t par,
                                                 long long* ts = nullptr, int dbg = 0) {
   const uint32_t tl = tm_base + (static_cast<uint32_t>(32 * wq) << 16);
@@ -279,7 +279,7 @@ __device__ __forceinline__ uint32_t ffn_tc_tile(float (&logit)[kNCls], uint32_t 
   if (!(dbg & 32)) { tc_mbar_wait(mma_bar, par); par ^= 1u; }
   tc_fence_after();
   VADB_TS(5);
-  if (!(dbg & 128)) tc_hidden_epilogue<kTcN1, HALVES>(tl, kTmD1, c_par.b1, hidx);
+  if (!(dbg & 128)) tc_hidden_epilogue<kTcN1, HALVES>(tl, kTmD1, fb.b1, hidx);
   VADB_TS(6);
   tc_fence_before();
   tc_bar<HALVES>();
@@ -291,7 +291,7 @@ __device__ __forceinline__ uint32_t ffn_tc_tile(float (&logit)[kNCls], uint32_t 
   if (!(dbg & 32)) { tc_mbar_wait(mma_bar, par); par ^= 1u; }
   tc_fence_after();
   VADB_TS(8);
-  if (!(dbg & 128)) tc_hidden_epilogue<kTcN2, HALVES>(tl, kTmD2, c_par.b2, hidx);
+  if (!(dbg & 128)) tc_hidden_epilogue<kTcN2, HALVES>(tl, kTmD2, fb.b2, hidx);
   VADB_TS(9);
   tc_fence_before();
   tc_bar<HALVES>();
@@ -303,7 +303,7 @@ __device__ __forceinline__ uint32_t ffn_tc_tile(float (&logit)[kNCls], uint32_t 
   if (!(dbg & 32)) { tc_mbar_wait(mma_bar, par); par ^= 1u; }
   tc_fence_after();
   VADB_TS(11);
-  if (!(dbg & 128)) tc_hidden_epilogue<kTcN3, HALVES>(tl, kTmD3, c_par.b3, hidx);
+  if (!(dbg & 128)) tc_hidden_epilogue<kTcN3, HALVES>(tl, kTmD3, fb.b3, hidx);
   VADB_TS(12);
   tc_fence_before();
   tc_bar<HALVES>();
@@ -321,7 +321,7 @@ __device__ __forceinline__ uint32_t ffn_tc_tile(float (&logit)[kNCls], uint32_t 
     tmem_ld8(tl + kTmD4 + kTcN4, u);
     tmem_wait_ld();
 #pragma unroll
-    for (int o = 0; o < kNCls; ++o) logit[o] = (__uint_as_float(v[o]) + __uint_as_float(u[o])) + c_par.b4[o];
+    for (int o = 0; o < kNCls; ++o) logit[o] = (__uint_as_float(v[o]) + __uint_as_float(u[o])) + fb.b4[o];
   }
   tc_fence_before();  // the next tile's tcgen05.st must not overtake these loads
   VADB_TS(15);

@@ -50,10 +50,19 @@ constexpr int kNCep = 13;        // config.py:26
 constexpr int kNFeat = 39;       // 13 x (mfcc, d1, d2)
 constexpr int kH1 = 64, kH2 = 32, kH3 = 16, kNCls = 3;  // ffn_trainer.py:108-115
 
-// ---- constant-memory parameter block (uniform operands of FFMA: c[bank][imm]) -------------
-struct ConstParams {
+// ---- parameter blocks ---------------------------------------------------------------------------
+// Mel / DCT tables depend only on the (single, compiled-in) reference configuration, so every
+// handle uploads bit-identical content: the __constant__ copy carries no per-handle state.
+struct MelDctTables {
   float melw[448];               // 444 non-zero triangle weights x 2^-20, filter-major (kMelOff)
   float dct[kNCep * kNMel];      // lifter[k] * dct2_ortho[k][n] * log10(2)   (input is log2 E)
+};
+VADB_CONSTANT MelDctTables c_tab;
+
+// FFN weights are per handle (one analyser == one classifier, sklearn_analyser.py:21-35): they
+// travel as a __grid_constant__ kernel parameter (constant bank 0: uniform FFMA operands), never
+// through device-global state.
+struct FfnParams {
   float W1[kNFeat * kH1];        // Keras (in,out) layout: y = x.W + b
   float b1[kH1];
   float W2[kH1 * kH2];
@@ -64,9 +73,48 @@ struct ConstParams {
   float b4[kNCls];
   float pad_[1];
 };
-VADB_CONSTANT ConstParams c_par;
+struct FfnBias {                 // what the tensor-core FFN needs besides its weight blob
+  float b1[kH1], b2[kH2], b3[kH3], b4[kNCls], pad_[1];
+};
+struct FfnNone { int unused; };
 
 struct cf2 { float x, y; };  // layout-compatible with float2 on both sides
+
+// ---- value types: float (one frame per thread) or f2 (two frames per thread, packed) ------------
+// sm_100a executes FFMA2 / FADD2 / FMUL2 on register pairs: one issue slot for two lanes of fp32
+// work, scalar operands broadcast for free (immediate, uniform register or R.F32).  The FFT code
+// below is written once over V; with V = f2 each thread carries the same butterfly for two frames.
+#if defined(__CUDACC__)
+using f2 = float2;
+#else
+struct f2 { float x, y; };
+#endif
+VADB_HD f2 mk2(float a, float b) { f2 r; r.x = a; r.y = b; return r; }
+VADB_HD f2 vneg(f2 a) { return mk2(-a.x, -a.y); }
+VADB_HD float vneg(float a) { return -a; }
+VADB_HD float vadd(float a, float b) { return a + b; }
+VADB_HD float vsub(float a, float b) { return a - b; }
+VADB_HD float vmul(float a, float b) { return a * b; }
+VADB_HD float vmuls(float s, float b) { return s * b; }
+VADB_HD float vfma(float a, float b, float c) { return fmaf(a, b, c); }
+VADB_HD float vfmas(float s, float b, float c) { return fmaf(s, b, c); }
+#if defined(__CUDA_ARCH__)
+VADB_HD f2 vadd(f2 a, f2 b) { return __fadd2_rn(a, b); }
+VADB_HD f2 vsub(f2 a, f2 b) { return __fadd2_rn(a, vneg(b)); }
+VADB_HD f2 vmul(f2 a, f2 b) { return __fmul2_rn(a, b); }
+VADB_HD f2 vmuls(float s, f2 b) { return __fmul2_rn(mk2(s, s), b); }
+VADB_HD f2 vfma(f2 a, f2 b, f2 c) { return __ffma2_rn(a, b, c); }
+VADB_HD f2 vfmas(float s, f2 b, f2 c) { return __ffma2_rn(mk2(s, s), b, c); }
+#else
+VADB_HD f2 vadd(f2 a, f2 b) { return mk2(a.x + b.x, a.y + b.y); }
+VADB_HD f2 vsub(f2 a, f2 b) { return mk2(a.x - b.x, a.y - b.y); }
+VADB_HD f2 vmul(f2 a, f2 b) { return mk2(a.x * b.x, a.y * b.y); }
+VADB_HD f2 vmuls(float s, f2 b) { return mk2(s * b.x, s * b.y); }
+VADB_HD f2 vfma(f2 a, f2 b, f2 c) { return mk2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+VADB_HD f2 vfmas(float s, f2 b, f2 c) { return mk2(fmaf(s, b.x, c.x), fmaf(s, b.y, c.y)); }
+#endif
+VADB_HD float vzero(float) { return 0.0f; }
+VADB_HD f2 vzero(f2) { return mk2(0.0f, 0.0f); }
 
 template <int B, int E, class F>
 VADB_HD void static_for(F&& f) {
@@ -77,38 +125,37 @@ VADB_HD void static_for(F&& f) {
 }
 
 // ---- radix-2 butterfly with compile-time twiddle W16^E:  o0 = a + w b,  o1 = a - w b -------
-template <int E>
-VADB_HD void bfly(float ar, float ai, float br, float bi, float& o0r, float& o0i, float& o1r,
-                  float& o1i) {
+template <int E, class V>
+VADB_HD void bfly(V ar, V ai, V br, V bi, V& o0r, V& o0i, V& o1r, V& o1i) {
   constexpr float C1 = 0.92387953251128674f;  // cos(pi/8)
   constexpr float S1 = 0.38268343236508977f;  // sin(pi/8)
   constexpr float R = 0.70710678118654752f;   // sqrt(1/2)
   if constexpr (E == 0) {
-    o0r = ar + br; o0i = ai + bi; o1r = ar - br; o1i = ai - bi;
+    o0r = vadd(ar, br); o0i = vadd(ai, bi); o1r = vsub(ar, br); o1i = vsub(ai, bi);
   } else if constexpr (E == 4) {  // w = -i : w b = (bi, -br)
-    o0r = ar + bi; o0i = ai - br; o1r = ar - bi; o1i = ai + br;
+    o0r = vadd(ar, bi); o0i = vsub(ai, br); o1r = vsub(ar, bi); o1i = vadd(ai, br);
   } else if constexpr (E == 2) {  // w = R(1 - i) : w b = R(br + bi) + i R(bi - br)
-    const float s = br + bi, d = bi - br;
-    o0r = fmaf(R, s, ar); o0i = fmaf(R, d, ai); o1r = fmaf(-R, s, ar); o1i = fmaf(-R, d, ai);
+    const V s = vadd(br, bi), d = vsub(bi, br);
+    o0r = vfmas(R, s, ar); o0i = vfmas(R, d, ai); o1r = vfmas(-R, s, ar); o1i = vfmas(-R, d, ai);
   } else if constexpr (E == 6) {  // w = R(-1 - i) : w b = R(bi - br) - i R(br + bi)
-    const float s = br + bi, d = bi - br;
-    o0r = fmaf(R, d, ar); o0i = fmaf(-R, s, ai); o1r = fmaf(-R, d, ar); o1i = fmaf(R, s, ai);
+    const V s = vadd(br, bi), d = vsub(bi, br);
+    o0r = vfmas(R, d, ar); o0i = vfmas(-R, s, ai); o1r = vfmas(-R, d, ar); o1i = vfmas(R, s, ai);
   } else {  // general: 6 FMA
     constexpr float wr = (E == 1) ? C1 : (E == 3) ? S1 : (E == 5) ? -S1 : -C1;
     constexpr float wi = (E == 1) ? -S1 : (E == 3) ? -C1 : (E == 5) ? -C1 : -S1;
-    float xr = fmaf(wr, br, ar); xr = fmaf(-wi, bi, xr);
-    float xi = fmaf(wr, bi, ai); xi = fmaf(wi, br, xi);
+    V xr = vfmas(wr, br, ar); xr = vfmas(-wi, bi, xr);
+    V xi = vfmas(wr, bi, ai); xi = vfmas(wi, br, xi);
     o0r = xr; o0i = xi;
-    o1r = fmaf(2.0f, ar, -xr); o1i = fmaf(2.0f, ai, -xi);
+    o1r = vfmas(2.0f, ar, vneg(xr)); o1i = vfmas(2.0f, ai, vneg(xi));
   }
 }
 
 // 16-point forward DFT (e^{-2 pi i nk/16}), natural order in and out, decimation in time.
 // Stage with sub-length m (G = 8/m classes): a = F_m,n[k] at n + 2Gk, b at a + G,
 // twiddle W16^(kG), results at n + Gk and n + Gk + 8.  Inputs with index >= NZ are zero.
-template <int NZ>
-VADB_HD void dft16(float (&xr)[16], float (&xi)[16]) {
-  float ar[16], ai[16];
+template <int NZ, class V>
+VADB_HD void dft16(V (&xr)[16], V (&xi)[16]) {
+  V ar[16], ai[16];
   static_for<0, 8>([&](auto N) {  // m = 1, G = 8
     constexpr int n = N;
     if constexpr (n + 8 < NZ) {
@@ -140,14 +187,28 @@ VADB_HD void dft16(float (&xr)[16], float (&xi)[16]) {
 // ---- pass 1: load, pruned DFT16, inter-pass twiddle -----------------------------------------
 // Packed int16 PCM: w32 points at the frame's first sample viewed as 32-bit words (sample
 // offset even); thread t takes complex samples t + 16 j (j = 12 only for t < 8: n < 200).
+VADB_HD float pcm_lo(uint32_t v) { return static_cast<float>(static_cast<int16_t>(v & 0xffffu)); }
+VADB_HD float pcm_hi(uint32_t v) { return static_cast<float>(static_cast<int16_t>(v >> 16)); }  // I2F.S16 Rx.H1
 VADB_HD void fft_load_pcm(const uint32_t* w32, int t, float (&xr)[16], float (&xi)[16]) {
   static_for<0, 13>([&](auto J) {
     constexpr int j = J;
     uint32_t v = (j < 12 || t < 8) ? w32[t + 16 * j] : 0u;
-    xr[j] = static_cast<float>(static_cast<int16_t>(v & 0xffffu));
-    xi[j] = static_cast<float>(static_cast<int32_t>(v) >> 16);
+    xr[j] = pcm_lo(v);
+    xi[j] = pcm_hi(v);
   });
   xr[13] = xi[13] = xr[14] = xi[14] = xr[15] = xi[15] = 0.0f;
+}
+// Two frames per thread: frame A at w32, frame B `delta` words further (same stage buffer).
+VADB_HD void fft_load_pcm2(const uint32_t* w32, int delta, int t, f2 (&xr)[16], f2 (&xi)[16]) {
+  static_for<0, 13>([&](auto J) {
+    constexpr int j = J;
+    const bool on = (j < 12 || t < 8);
+    const uint32_t va = on ? w32[t + 16 * j] : 0u;
+    const uint32_t vb = on ? w32[delta + t + 16 * j] : 0u;
+    xr[j] = mk2(pcm_lo(va), pcm_lo(vb));
+    xi[j] = mk2(pcm_hi(va), pcm_hi(vb));
+  });
+  xr[13] = xi[13] = xr[14] = xi[14] = xr[15] = xi[15] = mk2(0.0f, 0.0f);
 }
 
 // Explicit float32 frames (the reference's per-frame API takes float frames, vad.py:37).
@@ -161,30 +222,32 @@ VADB_HD void fft_load_f32(const float* fr, int frame_len, int t, float (&xr)[16]
   });
 }
 
-// tw1: [k1][t] = W256^(t k1).  TW1 is a callable (k1 -> cf2): shared-memory table reads in the
-// emulation / small kernels, per-thread register copies in the fused kernel (the table rows depend
-// only on t, and re-reading them every round was 25 % of the kernel's shared-memory traffic).
-template <int NZ, class TW1>
-VADB_HD void fft_pass1_tw(float (&xr)[16], float (&xi)[16], TW1&& tw1) {
+// tw1: [k1][t] = W256^(t k1).  TW1 is a callable (k1 -> cf2): shared-memory table reads.  The
+// twiddle is a per-thread scalar pair; with V = f2 it is broadcast to both frames (R.F32 operand).
+template <int NZ, class V, class TW1>
+VADB_HD void fft_pass1_tw(V (&xr)[16], V (&xi)[16], TW1&& tw1) {
   dft16<NZ>(xr, xi);
   static_for<1, 16>([&](auto K) {
     constexpr int k1 = K;
     const cf2 w = tw1(K);
-    const float r = xr[k1], i = xi[k1];
-    xr[k1] = fmaf(r, w.x, -(i * w.y));
-    xi[k1] = fmaf(r, w.y, i * w.x);
+    const V r = xr[k1], i = xi[k1];
+    xr[k1] = vfmas(w.x, r, vneg(vmuls(w.y, i)));
+    xi[k1] = vfmas(w.y, r, vmuls(w.x, i));
   });
 }
-template <int NZ>
-VADB_HD void fft_pass1(float (&xr)[16], float (&xi)[16], const cf2* tw1, int t) {
+template <int NZ, class V>
+VADB_HD void fft_pass1(V (&xr)[16], V (&xi)[16], const cf2* tw1, int t) {
   fft_pass1_tw<NZ>(xr, xi, [&](auto K) { return tw1[decltype(K)::value * 16 + t]; });
 }
 
 // 16x16 transpose buffer of one frame: row n2 = t (pass-1 thread), column k1; row pitch 17
-// complex (34 words): the 16 threads' 64-bit row stores land on banks 2t, 2t+1 and the 64-bit
-// column loads on consecutive words -- both bank-conflict free.
+// 64-bit slots (34 words): the 16 threads' 64-bit row stores land on banks 2t, 2t+1 and the 64-bit
+// column loads on consecutive words -- both bank-conflict free.  One frame per thread: a slot is
+// one complex value (re, im).  Two frames per thread: a slot is one component of both frames
+// (A, B), and the real and imaginary planes go through the same buffer one after the other
+// (exch_store_plane / exch_load_plane with a warp barrier between), so the scratch does not grow.
 constexpr int kExchPitch = 17;
-constexpr int kExchFrame = 16 * kExchPitch;  // cf2 elements per frame
+constexpr int kExchFrame = 16 * kExchPitch;  // 64-bit slots per half-warp
 
 VADB_HD void exch_store(cf2* ex, int t, const float (&xr)[16], const float (&xi)[16]) {
   static_for<0, 16>([&](auto K) {
@@ -199,17 +262,23 @@ VADB_HD void exch_load(const cf2* ex, int k1, float (&xr)[16], float (&xi)[16]) 
     xr[n2] = v.x; xi[n2] = v.y;
   });
 }
+VADB_HD void exch_store_plane(f2* ex, int t, const f2 (&x)[16]) {
+  static_for<0, 16>([&](auto K) { ex[t * kExchPitch + decltype(K)::value] = x[decltype(K)::value]; });
+}
+VADB_HD void exch_load_plane(const f2* ex, int k1, f2 (&x)[16]) {
+  static_for<0, 16>([&](auto N) { x[decltype(N)::value] = ex[decltype(N)::value * kExchPitch + k1]; });
+}
 
 // ---- real-FFT split of one bin pair (k, 256-k); returns |2 X[k]|^2 and |2 X[256-k]|^2 -------
-VADB_HD void split_pair(float ar, float ai, float br, float bi, float wr, float wi, float& plo,
-                        float& phi) {
-  const float er = ar + br, ei = ai - bi;    // E = a + conj(b)
-  const float qr = ai + bi, qi = br - ar;    // O = -i (a - conj(b))
-  float xr = fmaf(wr, qr, er); xr = fmaf(-wi, qi, xr);   // 2 X[k] = E + w O
-  float xi = fmaf(wr, qi, ei); xi = fmaf(wi, qr, xi);
-  const float yr = fmaf(2.0f, er, -xr), yi = fmaf(2.0f, ei, -xi);  // 2 conj X[256-k] = E - w O
-  plo = fmaf(xr, xr, xi * xi);
-  phi = fmaf(yr, yr, yi * yi);
+template <class V>
+VADB_HD void split_pair(V ar, V ai, V br, V bi, float wr, float wi, V& plo, V& phi) {
+  const V er = vadd(ar, br), ei = vsub(ai, bi);    // E = a + conj(b)
+  const V qr = vadd(ai, bi), qi = vsub(br, ar);    // O = -i (a - conj(b))
+  V xr = vfmas(wr, qr, er); xr = vfmas(-wi, qi, xr);   // 2 X[k] = E + w O
+  V xi = vfmas(wr, qi, ei); xi = vfmas(wi, qr, xi);
+  const V yr = vfmas(2.0f, er, vneg(xr)), yi = vfmas(2.0f, ei, vneg(xi));  // 2 conj X[256-k] = E - w O
+  plo = vfma(xr, xr, vmul(xi, xi));
+  phi = vfma(yr, yr, vmul(yi, yi));
 }
 
 // After pass 2 thread k1 holds Z[k1 + 16 k2] in (xr[k2], xi[k2]).  It finishes the 8 pairs
@@ -221,10 +290,10 @@ VADB_HD void split_pair(float ar, float ai, float br, float bi, float wr, float 
 #if defined(__CUDACC__)
 #pragma nv_exec_check_disable
 #endif
-template <class TW2, class XCH, class STORE>
-VADB_HD void fft_split_store_tw(const float (&xr)[16], const float (&xi)[16], int k1, TW2&& tw2,
+template <class V, class TW2, class XCH, class STORE>
+VADB_HD void fft_split_store_tw(const V (&xr)[16], const V (&xi)[16], int k1, TW2&& tw2,
                                 XCH&& xch, STORE&& store) {
-  float sr[16], si[16];
+  V sr[16], si[16];
   static_for<8, 16>([&](auto J) {
     constexpr int j = J;
     sr[j] = (k1 == 0) ? xr[(j + 1) & 15] : xr[j];
@@ -233,22 +302,22 @@ VADB_HD void fft_split_store_tw(const float (&xr)[16], const float (&xi)[16], in
   const int partner = (16 - k1) & 15;
   static_for<0, 8>([&](auto K) {
     constexpr int k2 = K;
-    const float br = xch(sr[15 - k2], 15 - k2, false, partner);
-    const float bi = xch(si[15 - k2], 15 - k2, true, partner);
+    const V br = xch(sr[15 - k2], 15 - k2, false, partner);
+    const V bi = xch(si[15 - k2], 15 - k2, true, partner);
     const cf2 w = tw2(K);  // W512^(k1 + 16 k2)
-    float plo, phi;
+    V plo, phi;
     split_pair(xr[k2], xi[k2], br, bi, w.x, w.y, plo, phi);
     const int lo = k1 + 16 * k2;
     store(lo, plo);
     if (k2 != 0 || k1 != 0) store(256 - lo, phi);
   });
-  if (k1 == 0) store(128, 4.0f * fmaf(xr[8], xr[8], xi[8] * xi[8]));
+  if (k1 == 0) store(128, vmuls(4.0f, vfma(xr[8], xr[8], vmul(xi[8], xi[8]))));
 }
 #if defined(__CUDACC__)
 #pragma nv_exec_check_disable
 #endif
-template <class XCH, class STORE>
-VADB_HD void fft_split_store(const float (&xr)[16], const float (&xi)[16], int k1, const cf2* tw2,
+template <class V, class XCH, class STORE>
+VADB_HD void fft_split_store(const V (&xr)[16], const V (&xi)[16], int k1, const cf2* tw2,
                              XCH&& xch, STORE&& store) {
   fft_split_store_tw(xr, xi, k1, [&](auto K) { return tw2[decltype(K)::value * 16 + k1]; }, xch, store);
 }
@@ -274,7 +343,7 @@ VADB_HD void mel_group(const float* P, float* logE) {
       constexpr int k = K;
       constexpr int c = (k - lo) & 3;
       const float pw = P[k * PITCH];
-      const float w = c_par.melw[off + k - lo];
+      const float w = c_tab.melw[off + k - lo];
       if constexpr (c == 0) e0 = fmaf(pw, w, e0);
       else if constexpr (c == 1) e1 = fmaf(pw, w, e1);
       else if constexpr (c == 2) e2 = fmaf(pw, w, e2);
@@ -306,13 +375,13 @@ VADB_HD float dct_coef(const float* logE, int c) {
   float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;  // four chains instead of one 26-long one
 #pragma unroll
   for (int n = 0; n < 24; n += 4) {
-    a0 = fmaf(logE[(n + 0) * PITCH], c_par.dct[c * kNMel + n + 0], a0);
-    a1 = fmaf(logE[(n + 1) * PITCH], c_par.dct[c * kNMel + n + 1], a1);
-    a2 = fmaf(logE[(n + 2) * PITCH], c_par.dct[c * kNMel + n + 2], a2);
-    a3 = fmaf(logE[(n + 3) * PITCH], c_par.dct[c * kNMel + n + 3], a3);
+    a0 = fmaf(logE[(n + 0) * PITCH], c_tab.dct[c * kNMel + n + 0], a0);
+    a1 = fmaf(logE[(n + 1) * PITCH], c_tab.dct[c * kNMel + n + 1], a1);
+    a2 = fmaf(logE[(n + 2) * PITCH], c_tab.dct[c * kNMel + n + 2], a2);
+    a3 = fmaf(logE[(n + 3) * PITCH], c_tab.dct[c * kNMel + n + 3], a3);
   }
-  a0 = fmaf(logE[24 * PITCH], c_par.dct[c * kNMel + 24], a0);
-  a1 = fmaf(logE[25 * PITCH], c_par.dct[c * kNMel + 25], a1);
+  a0 = fmaf(logE[24 * PITCH], c_tab.dct[c * kNMel + 24], a0);
+  a1 = fmaf(logE[25 * PITCH], c_tab.dct[c * kNMel + 25], a1);
   return (a0 + a2) + (a1 + a3);
 }
 
@@ -324,14 +393,14 @@ VADB_HD void dct_coef2(const float* logE, int ca, int cb, float& ra, float& rb) 
   for (int n = 0; n < 24; n += 4) {
     const float l0 = logE[(n + 0) * PITCH], l1 = logE[(n + 1) * PITCH], l2 = logE[(n + 2) * PITCH],
                 l3 = logE[(n + 3) * PITCH];
-    a0 = fmaf(l0, c_par.dct[ca * kNMel + n + 0], a0); b0 = fmaf(l0, c_par.dct[cb * kNMel + n + 0], b0);
-    a1 = fmaf(l1, c_par.dct[ca * kNMel + n + 1], a1); b1 = fmaf(l1, c_par.dct[cb * kNMel + n + 1], b1);
-    a2 = fmaf(l2, c_par.dct[ca * kNMel + n + 2], a2); b2 = fmaf(l2, c_par.dct[cb * kNMel + n + 2], b2);
-    a3 = fmaf(l3, c_par.dct[ca * kNMel + n + 3], a3); b3 = fmaf(l3, c_par.dct[cb * kNMel + n + 3], b3);
+    a0 = fmaf(l0, c_tab.dct[ca * kNMel + n + 0], a0); b0 = fmaf(l0, c_tab.dct[cb * kNMel + n + 0], b0);
+    a1 = fmaf(l1, c_tab.dct[ca * kNMel + n + 1], a1); b1 = fmaf(l1, c_tab.dct[cb * kNMel + n + 1], b1);
+    a2 = fmaf(l2, c_tab.dct[ca * kNMel + n + 2], a2); b2 = fmaf(l2, c_tab.dct[cb * kNMel + n + 2], b2);
+    a3 = fmaf(l3, c_tab.dct[ca * kNMel + n + 3], a3); b3 = fmaf(l3, c_tab.dct[cb * kNMel + n + 3], b3);
   }
   const float l24 = logE[24 * PITCH], l25 = logE[25 * PITCH];
-  a0 = fmaf(l24, c_par.dct[ca * kNMel + 24], a0); b0 = fmaf(l24, c_par.dct[cb * kNMel + 24], b0);
-  a1 = fmaf(l25, c_par.dct[ca * kNMel + 25], a1); b1 = fmaf(l25, c_par.dct[cb * kNMel + 25], b1);
+  a0 = fmaf(l24, c_tab.dct[ca * kNMel + 24], a0); b0 = fmaf(l24, c_tab.dct[cb * kNMel + 24], b0);
+  a1 = fmaf(l25, c_tab.dct[ca * kNMel + 25], a1); b1 = fmaf(l25, c_tab.dct[cb * kNMel + 25], b1);
   ra = (a0 + a2) + (a1 + a3);
   rb = (b0 + b2) + (b1 + b3);
 }
@@ -372,15 +441,15 @@ VADB_HD bool window_features(const float (&r)[5][kNCep], int mode, float (&x)[kN
 
 // Features of the coefficient range [K0, K1) only, ordered (k, g): out[3 (k-K0) + g] with g = 0 z,
 // 1 d1, 2 d2 -- the layer-1 column order of the tensor-core FFN (ffn_tc.cuh: tc_feat_col).
-// ring: MFCC ring [coef][RING]; centre frame c.  Same arithmetic as window_features.
-template <int K0, int K1, int RING, int NOUT>
+// ring: MFCC ring [coef][PITCH], RING slots used; centre frame c.  Same arithmetic as window_features.
+template <int K0, int K1, int RING, int PITCH, int NOUT>
 VADB_HD bool window_features_range(const float* ring, int c, int mode, float (&out)[NOUT]) {
   bool ok = true;
   static_assert(3 * (K1 - K0) <= NOUT, "output too small");
   const int c0i = (c - 2) % RING, c1i = (c - 1) % RING, c2i = c % RING, c3i = (c + 1) % RING, c4i = (c + 2) % RING;
 #pragma unroll
   for (int k = K0; k < K1; ++k) {
-    const float* row = ring + k * RING;
+    const float* row = ring + k * PITCH;
     const float c0 = row[c0i], c1 = row[c1i], c2 = row[c2i], c3 = row[c3i], c4 = row[c4i];
     float z = c2;
     if (mode == 0) {
@@ -400,46 +469,46 @@ VADB_HD bool window_features_range(const float* ring, int c, int mode, float (&o
   return ok;
 }
 
-// ---- FFN forward, one frame per thread, weights as uniform constant operands -------------------
-VADB_HD void ffn_forward(const float (&x)[kNFeat], float (&logit)[kNCls]) {
+// ---- FFN forward, one frame per thread, weights as uniform constant operands (w = kernel parameter) -------------------
+VADB_HD void ffn_forward(const FfnParams& w, const float (&x)[kNFeat], float (&logit)[kNCls]) {
   float h2[kH2];
 #pragma unroll
-  for (int o = 0; o < kH2; ++o) h2[o] = c_par.b2[o];
+  for (int o = 0; o < kH2; ++o) h2[o] = w.b2[o];
   // Rolled on purpose: the fully unrolled FFN (134 KB of SASS) thrashed the instruction cache
   // (ncu: 33 % stall_no_inst in this phase); one 8-neuron body is ~12 KB.
 #pragma unroll 1
   for (int c = 0; c < kH1 / 8; ++c) {  // 8 layer-1 neurons at a time, streamed into layer 2
     float h1[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) h1[j] = c_par.b1[8 * c + j];
+    for (int j = 0; j < 8; ++j) h1[j] = w.b1[8 * c + j];
 #pragma unroll
     for (int i = 0; i < kNFeat; ++i) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) h1[j] = fmaf(x[i], c_par.W1[i * kH1 + 8 * c + j], h1[j]);
+      for (int j = 0; j < 8; ++j) h1[j] = fmaf(x[i], w.W1[i * kH1 + 8 * c + j], h1[j]);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float a = fmaxf(h1[j], 0.0f);  // the duplicate ReLU (ffn_trainer.py:110) is idempotent
 #pragma unroll
-      for (int o = 0; o < kH2; ++o) h2[o] = fmaf(a, c_par.W2[(8 * c + j) * kH2 + o], h2[o]);
+      for (int o = 0; o < kH2; ++o) h2[o] = fmaf(a, w.W2[(8 * c + j) * kH2 + o], h2[o]);
     }
   }
   float h3[kH3];
 #pragma unroll
-  for (int o = 0; o < kH3; ++o) h3[o] = c_par.b3[o];
+  for (int o = 0; o < kH3; ++o) h3[o] = w.b3[o];
 #pragma unroll
   for (int i = 0; i < kH2; ++i) {
     const float a = fmaxf(h2[i], 0.0f);
 #pragma unroll
-    for (int o = 0; o < kH3; ++o) h3[o] = fmaf(a, c_par.W3[i * kH3 + o], h3[o]);
+    for (int o = 0; o < kH3; ++o) h3[o] = fmaf(a, w.W3[i * kH3 + o], h3[o]);
   }
 #pragma unroll
-  for (int o = 0; o < kNCls; ++o) logit[o] = c_par.b4[o];
+  for (int o = 0; o < kNCls; ++o) logit[o] = w.b4[o];
 #pragma unroll
   for (int i = 0; i < kH3; ++i) {
     const float a = fmaxf(h3[i], 0.0f);
 #pragma unroll
-    for (int o = 0; o < kNCls; ++o) logit[o] = fmaf(a, c_par.W4[i * kNCls + o], logit[o]);
+    for (int o = 0; o < kNCls; ++o) logit[o] = fmaf(a, w.W4[i * kNCls + o], logit[o]);
   }
 }
 

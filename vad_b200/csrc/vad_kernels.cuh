@@ -5,9 +5,11 @@
 //   1. PCM for the step (5360 int16 = 31 hops + one frame) arrives in shared memory by one
 //      TMA bulk copy (cp.async.bulk + mbarrier), double-buffered one step ahead; overlapping
 //      frames are re-read from shared memory, never from HBM.
-//   2. FFT phase: each warp transforms 4 frames (2 rounds x 2 frames, 16 threads per frame):
-//      pruned DFT16 -> twiddle -> 16x16 transpose in shared memory -> DFT16 -> partner shuffle
-//      -> real-FFT split -> |X|^2 into the P tile [256 bins][32 frames].
+//   2. FFT phase: each warp transforms 4 frames in ONE pass: a half-warp (16 threads) carries two
+//      frames per thread as packed register pairs, so every butterfly / twiddle / split / power
+//      operation is one FFMA2 / FADD2 / FMUL2 for both frames (sm_100a packed fp32):
+//      pruned DFT16 -> twiddle -> 16x16 transpose in shared memory (re plane, then im plane)
+//      -> DFT16 -> partner shuffle -> real-FFT split -> |X|^2 into the P tile [256 bins][32 cols].
 //   3. mel + log phase: lane = frame, warp = one of 8 balanced filter groups; weights are
 //      constant-bank FFMA operands; exact-zero -> eps; log2.
 //   4. DCT phase: lane = frame, warp = coefficient; folded DCT-II x lifter x log10(2) matrix;
@@ -30,7 +32,8 @@ namespace vadb {
 constexpr int kThreads = 256;
 constexpr int kWarps = 8;
 constexpr int kStepFrames = 32;
-constexpr int kRing = 288;
+constexpr int kRing = 288;                                     // MFCC ring slots (modulus)
+constexpr int kRingPitch = kRing + 1;                          // odd row pitch: coefficient-strided reads spread over banks
 constexpr int kPPitch = 34;                                    // == 2 (mod 32): conflict-free P stores
 constexpr int kStageSamples = (kStepFrames - 1) * kHop + kFrame;  // 5360
 constexpr int kStagePad = 5376;                                // samples; 10752 B, 128-B multiple
@@ -41,7 +44,7 @@ constexpr int kOffExch = kOffPcm + 2 * kStagePad * 2;                       // 2
 constexpr int kOffP = kOffExch + kWarps * 2 * kExchFrame * 8;               // + 34816
 constexpr int kOffLogE = kOffP + kBins * kPPitch * 4;                       // + 34816
 constexpr int kOffRing = kOffLogE + kNMel * 32 * 4;                         // + 3328
-constexpr int kOffTw1 = kOffRing + kNCep * kRing * 4;                       // + 14976
+constexpr int kOffTw1 = kOffRing + ((kNCep * kRingPitch * 4 + 15) & ~15);   // + 15040
 constexpr int kOffTw2 = kOffTw1 + 256 * 8;
 constexpr int kOffBar = kOffTw2 + 128 * 8;
 constexpr int kOffSeg = kOffBar + 32;                                       // 4 mbarriers: pcm x2, weights, mma
@@ -69,7 +72,7 @@ struct FusedParams {
   long long pcm_len;      // one past the last readable sample index (relative to pcm)
   const Segment* segs;
   int seg_begin, seg_end;
-  int* counter;
+  int* counter;           // counter[0]: next segment, counter[1]: CTAs finished (the last one resets both)
   const cf2* tw1;
   const cf2* tw2;
   uint8_t* labels;
@@ -125,7 +128,40 @@ struct ShflXchg {
   __device__ __forceinline__ float operator()(float mine, int, bool, int partner) const {
     return __shfl_sync(0xffffffffu, mine, (lane & 16) | partner);
   }
+  __device__ __forceinline__ f2 operator()(f2 mine, int, bool, int partner) const {
+    const int src = (lane & 16) | partner;
+    return mk2(__shfl_sync(0xffffffffu, mine.x, src), __shfl_sync(0xffffffffu, mine.y, src));
+  }
 };
+
+// P-tile column of frame slot fs inside a 32-frame step.  A half-warp carries frame slots
+// 4w + h and 4w + h + 2 (so that the two half-warps' PCM reads fall on different banks) and stores
+// their powers side by side as one 64-bit word: columns 4w + 2h, 4w + 2h + 1.
+__host__ __device__ __forceinline__ int slot_of_col(int c) { return (c & ~3) | ((c >> 1) & 1) | ((c & 1) << 1); }
+
+// Four frames of a warp through the FFT: half-warp h = lanes 16h..16h+15, two frames per thread.
+// w32a: first PCM word of frame A; frame B starts `delta` words later.  ex: this half-warp's
+// transpose scratch (kExchFrame 64-bit slots).  Powers go to P columns col, col + 1.
+template <int NZ>
+__device__ __forceinline__ void warp_fft_quad(const uint32_t* w32a, int delta, f2* ex, const cf2* s_tw1,
+                                               const cf2* s_tw2, float* s_P, int col, int lane) {
+  const int t = lane & 15;
+  f2 xr[16], xi[16];
+  fft_load_pcm2(w32a, delta, t, xr, xi);
+  fft_pass1<NZ>(xr, xi, s_tw1, t);
+  exch_store_plane(ex, t, xr);
+  __syncwarp();
+  exch_load_plane(ex, t, xr);
+  __syncwarp();
+  exch_store_plane(ex, t, xi);
+  __syncwarp();
+  exch_load_plane(ex, t, xi);
+  __syncwarp();
+  dft16<16>(xr, xi);
+  fft_split_store(xr, xi, t, s_tw2, ShflXchg{lane}, [&](int bin, f2 v) {
+    *reinterpret_cast<f2*>(s_P + bin * kPPitch + col) = v;
+  });
+}
 
 // Both frames of a warp (lanes 0-15 / 16-31) through the FFT; P column = frame slot fi.
 template <int NZ, class LOAD>
@@ -143,13 +179,36 @@ __device__ __forceinline__ void warp_fft_pair(LOAD&& load, cf2* ex, const cf2* s
   fft_split_store(xr, xi, t, s_tw2, ShflXchg{lane}, [&](int bin, float v) { s_P[bin * kPPitch + fi] = v; });
 }
 
+// Coalesced store of `total` consecutive floats starting at dst: a scalar head up to the first 16-byte
+// boundary, 128-bit stores, scalar tail.  gen(j, v, cnt) produces elements j .. j + cnt - 1 (cnt <= 4).
+template <class GEN>
+__device__ __forceinline__ void flush_flat(float* dst, int total, int tid, GEN&& gen) {
+  if (total <= 0) return;
+  const int head = min(total, static_cast<int>((16u - (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u) >> 2);
+  const int nq = (total - head) >> 2;
+  for (int q = tid; q < nq; q += kThreads) {
+    float v[4];
+    gen(head + 4 * q, v, 4);
+    *reinterpret_cast<float4*>(dst + head + 4 * q) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  const int tail0 = head + 4 * nq;
+  if (tid < 2) {  // thread 0: head, thread 1: tail (each < 4 elements)
+    const int j0 = tid == 0 ? 0 : tail0, cnt = tid == 0 ? head : total - tail0;
+    if (cnt > 0) {
+      float v[4];
+      gen(j0, v, cnt);
+      for (int i = 0; i < cnt; ++i) dst[j0 + i] = v[i];
+    }
+  }
+}
+
 // One output row per thread: window features -> FFN -> decision (block phase / windows API).
-__device__ __forceinline__ void classify_row(const float (&r)[5][kNCep], int feat_mode, uint8_t* labels,
-                                             float* logits, float* feats, long long row) {
+__device__ __forceinline__ void classify_row(const FfnParams& w, const float (&r)[5][kNCep], int feat_mode,
+                                             uint8_t* labels, float* logits, float* feats, long long row) {
   float x[kNFeat];
   const bool ok = window_features(r, feat_mode, x);
   float logit[kNCls];
-  ffn_forward(x, logit);
+  ffn_forward(w, x, logit);
   uint8_t lab = decide(logit);
   if (!ok) {
     logit[0] = logit[1] = logit[2] = NAN;
@@ -169,8 +228,15 @@ __device__ __forceinline__ void classify_row(const float (&r)[5][kNCep], int fea
 
 // MODE 0: MFCC rows [T][13]; 1: dataset rows [T-5][39]; 2: VAD labels [T-5].
 // TC (MODE 2 only): 0 = FFN on FP32 CUDA cores, 1 = FFN on tcgen05 (tf32 x3, TMEM accumulators).
+// FFN argument of the kernel variant: nothing (MFCC / dataset rows), the full FP32 weights, or the biases
+// only (tensor-core FFN: the weights are the per-handle tcgen05 operand blob in global memory).
+template <int MODE, int TC> struct FfnArgOf { using type = FfnNone; };
+template <> struct FfnArgOf<2, 0> { using type = FfnParams; };
+template <> struct FfnArgOf<2, 1> { using type = FfnBias; };
+
 template <int MODE, int TC>
-__global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constant__ FusedParams p,
+                                                            const __grid_constant__ typename FfnArgOf<MODE, TC>::type ffn) {
   static_assert(TC == 0 || MODE == 2, "tensor-core FFN only exists in VAD mode");
   constexpr int kBlk = TC ? kBlockStepsTc : kBlockSteps;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -246,16 +312,11 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
 
       // ---- FFT phase ---------------------------------------------------------------------
       const uint32_t* stage32 = reinterpret_cast<const uint32_t*>(s_pcm + buf * kStagePad);
-      cf2* ex = s_exch + (warp * 2 + h) * kExchFrame;
-#pragma unroll 1
-      for (int r = 0; r < 2; ++r) {
-        if (VADB_DBG(p) & 1) break;
-        const int fi = warp * 4 + r * 2 + h;
-        const uint32_t* w32 = stage32 + fi * (kHop / 2);
-        // (keeping the 46 twiddle values in registers instead of re-reading the shared tables was
-        // measured neutral for the TC variant and spilled in the FP32-FFN variant: not used)
-        warp_fft_pair<13>([&](float (&xr)[16], float (&xi)[16]) { fft_load_pcm(w32, t, xr, xi); }, ex, s_tw1,
-                          s_tw2, s_P, fi, lane);
+      if (!(VADB_DBG(p) & 1)) {
+        // half-warp h: frame slots 4 warp + h and + 2 (PCM 80 words apart per slot -> the two half-warps
+        // read different banks), P columns 4 warp + 2 h, + 1
+        f2* ex = reinterpret_cast<f2*>(s_exch) + (warp * 2 + h) * kExchFrame;
+        warp_fft_quad<13>(stage32 + (warp * 4 + h) * (kHop / 2), kHop, ex, s_tw1, s_tw2, s_P, warp * 4 + 2 * h, lane);
       }
       __syncthreads();
 
@@ -273,43 +334,52 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
 
       // ---- DCT phase -> MFCC ring -----------------------------------------------------------
       if (!(VADB_DBG(p) & 4)) {
-        const int col = (s * kStepFrames + lane) % kRing;
+        const int col = (s * kStepFrames + slot_of_col(lane)) % kRing;  // lane = P column
         if (warp + 8 < kNCep) {
           float ra, rb;
           dct_coef2<32>(s_logE + lane, warp, warp + 8, ra, rb);
-          s_ring[warp * kRing + col] = ra;
-          s_ring[(warp + 8) * kRing + col] = rb;
+          s_ring[warp * kRingPitch + col] = ra;
+          s_ring[(warp + 8) * kRingPitch + col] = rb;
         } else {
-          s_ring[warp * kRing + col] = dct_coef<32>(s_logE + lane, warp);
+          s_ring[warp * kRingPitch + col] = dct_coef<32>(s_logE + lane, warp);
         }
       }
 
       if (block_now) {
         __syncthreads();
         if (MODE == 0) {
-          const long long base = (seg.out_start - p.row_base + out_done) * kNCep;
-          const int total = (computed - out_done) * kNCep;
-          for (int j = tid; j < total; j += kThreads) {
-            const int fr = j / kNCep, cf = j - fr * kNCep;
-            p.rows[base + j] = s_ring[cf * kRing + (out_done + fr) % kRing];
-          }
+          // rows are contiguous in global memory: flat float index j <-> (frame j / 13, coefficient j % 13)
+          float* dst = p.rows + (seg.out_start - p.row_base + out_done) * kNCep;
+          const int first = out_done;
+          flush_flat(dst, (computed - out_done) * kNCep, tid, [&](int j, float (&v)[4], int cnt) {
+            int fr = j / kNCep, cf = j - fr * kNCep;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (i < cnt) v[i] = s_ring[cf * kRingPitch + (first + fr) % kRing];
+              if (++cf == kNCep) { cf = 0; ++fr; }
+            }
+          });
           out_done = computed;
         } else if (MODE == 1) {
           const int last = computed - 3;  // centres out_done .. last
-          const long long base = (seg.out_start - p.row_base + (out_done - 2)) * kNFeat;
-          const int total = (last - out_done + 1) * kNFeat;
-          for (int j = tid; j < total; j += kThreads) {
-            const int rr = j / kNFeat, col = j - rr * kNFeat;
-            const int grp = col / kNCep, cf = col - grp * kNCep;
-            const int c = out_done + rr;
-            const float* row = s_ring + cf * kRing;
-            const float c2 = row[c % kRing];
-            float v;
-            if (grp == 0) v = c2;
-            else if (grp == 1) v = row[(c + 1) % kRing] - row[(c - 1) % kRing];
-            else v = (row[(c + 2) % kRing] - c2) - (c2 - row[(c - 2) % kRing]);
-            p.rows[base + j] = v;
-          }
+          float* dst = p.rows + (seg.out_start - p.row_base + (out_done - 2)) * kNFeat;
+          const int first = out_done;
+          flush_flat(dst, (last - out_done + 1) * kNFeat, tid, [&](int j, float (&v)[4], int cnt) {
+            int rr = j / kNFeat, col = j - rr * kNFeat;
+            int grp = col / kNCep, cf = col - grp * kNCep;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (i < cnt) {
+                const int c = first + rr;
+                const float* row = s_ring + cf * kRingPitch;
+                const float c2 = row[c % kRing];
+                v[i] = grp == 0 ? c2
+                     : grp == 1 ? row[(c + 1) % kRing] - row[(c - 1) % kRing]
+                                : (row[(c + 2) % kRing] - c2) - (c2 - row[(c - 2) % kRing]);
+              }
+              if (++cf == kNCep) { cf = 0; if (++grp == 3) { grp = 0; ++rr; } }
+            }
+          });
           out_done = max(out_done, last + 1);
         } else if (!TC) {
           const int c = out_done + tid;
@@ -319,9 +389,10 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
             for (int d = 0; d < 5; ++d) {
               const int col = (c - 2 + d) % kRing;
 #pragma unroll
-              for (int k = 0; k < kNCep; ++k) r[d][k] = s_ring[k * kRing + col];
+              for (int k = 0; k < kNCep; ++k) r[d][k] = s_ring[k * kRingPitch + col];
             }
-            classify_row(r, p.feat_mode, p.labels, p.logits, p.feats, seg.out_start - p.row_base + (c - 2));
+            if constexpr (MODE == 2 && TC == 0)
+              classify_row(ffn, r, p.feat_mode, p.labels, p.logits, p.feats, seg.out_start - p.row_base + (c - 2));
           }
           out_done = max(out_done, computed - 2);
         } else {
@@ -349,8 +420,8 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
 #pragma unroll
                 for (int i = 0; i < 24; ++i) xl[i] = 0.5f;
               } else {
-                ok_half = (hidx == 0) ? window_features_range<0, 7, kRing, 24>(s_ring, c, p.feat_mode, xl)
-                                      : window_features_range<7, 13, kRing, 24>(s_ring, c, p.feat_mode, xl);
+                ok_half = (hidx == 0) ? window_features_range<0, 7, kRing, kRingPitch, 24>(s_ring, c, p.feat_mode, xl)
+                                      : window_features_range<7, 13, kRing, kRingPitch, 24>(s_ring, c, p.feat_mode, xl);
               }
               s_logE[tid] = ok_half ? 1.0f : 0.0f;
               if (ts) ts[1] = clock64();
@@ -364,8 +435,9 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
               }
               if (!(VADB_DBG(p) & 16)) mbar_wait(&s_bar[2], w_par);  // weight blob landed (issued before the DCT phase)
               if (ts) ts[2] = clock64();
-              mma_par = ffn_tc_tile<2>(logit, tm_base, warp & 3, hidx, tid == 0, smem_u32(wdst), &s_bar[3], mma_par, ts,
-                                       VADB_DBG(p));
+              if constexpr (TC == 1)
+                mma_par = ffn_tc_tile<2>(ffn, logit, tm_base, warp & 3, hidx, tid == 0, smem_u32(wdst), &s_bar[3], mma_par,
+                                         ts, VADB_DBG(p));
               ++dbg_n;
               if (valid && hidx == 0) {
                 const bool ok = s_logE[fr] != 0.0f && s_logE[128 + fr] != 0.0f;  // ordered by the tile's bar.syncs
@@ -396,13 +468,24 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const FusedParams p)
     __syncthreads();
     if (warp == 0) tmem_dealloc(tm_base, kTmemCols);
   }
+  // Every CTA reaches this point only after the work counter ran past seg_end, so the last one to
+  // arrive can re-arm the counter pair for the plan's next launch (no memset between launches).
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(p.counter + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+      p.counter[0] = 0;
+      p.counter[1] = 0;
+      __threadfence();
+    }
+  }
 }
 
 // Stand-alone tensor-core FFN over feature rows [n][39] (classifier.predict duck type): one CTA =
 // one 128-row tile.  Same tile routine as the fused kernel's block phase.
 constexpr int kFfnTcSmemBytes = kTcBlobBytes + 64;
 __global__ void __launch_bounds__(128) ffn_tc_rows_kernel(const float* x, long long n, const unsigned char* blob,
-                                                          uint8_t* labels, float* logits) {
+                                                          uint8_t* labels, float* logits,
+                                                          const __grid_constant__ FfnBias fb) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcBlobBytes);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kTcBlobBytes + 32);
@@ -438,8 +521,6 @@ __global__ void __launch_bounds__(128) ffn_tc_rows_kernel(const float* x, long l
     for (int i = 0; i < 24; ++i) h0[i] = h1[i] = 0.0f;
 #pragma unroll
     for (int f = 0; f < kNFeat; ++f) {
-      constexpr int dummy = 0;
-      (void)dummy;
       const int col = tc_feat_col(f);
       if (col < 24) h0[col] = v[f];
       else h1[col - 24] = v[f];
@@ -447,7 +528,7 @@ __global__ void __launch_bounds__(128) ffn_tc_rows_kernel(const float* x, long l
     tc_store_a1_half(tl, 0, h0);
     tc_store_a1_half(tl, 1, h1);
   }
-  ffn_tc_tile<1>(logit, tm_base, warp, 0, tid == 0, smem_u32(smem), &bars[1], 0);
+  ffn_tc_tile<1>(fb, logit, tm_base, warp, 0, tid == 0, smem_u32(smem), &bars[1], 0);
   if (i < n) {
     uint8_t lab = decide(logit);
     if (!ok) {
@@ -605,7 +686,7 @@ __global__ void __launch_bounds__(kThreads) spec_to_mfcc_kernel(const float* spe
 
 // 5-frame MFCC windows [n][5][13] -> features / logits / labels (one thread per window).
 __global__ void __launch_bounds__(128) windows_kernel(const float* win, long long n, int feat_mode, uint8_t* labels,
-                                                      float* logits, float* feats) {
+                                                      float* logits, float* feats, const __grid_constant__ FfnParams w) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float r[5][kNCep];
@@ -613,11 +694,12 @@ __global__ void __launch_bounds__(128) windows_kernel(const float* win, long lon
   for (int d = 0; d < 5; ++d)
 #pragma unroll
     for (int k = 0; k < kNCep; ++k) r[d][k] = win[(i * 5 + d) * kNCep + k];
-  classify_row(r, feat_mode, labels, logits, feats, i);
+  classify_row(w, r, feat_mode, labels, logits, feats, i);
 }
 
 // classifier.predict duck type (sklearn_analyser.py:71): rows [n][39] -> class {0,1}, logits.
-__global__ void __launch_bounds__(128) ffn_rows_kernel(const float* x, long long n, uint8_t* labels, float* logits) {
+__global__ void __launch_bounds__(128) ffn_rows_kernel(const float* x, long long n, uint8_t* labels, float* logits,
+                                                       const __grid_constant__ FfnParams w) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float v[kNFeat];
@@ -628,7 +710,7 @@ __global__ void __launch_bounds__(128) ffn_rows_kernel(const float* x, long long
     ok = ok && (fabsf(v[k]) <= 3.0e38f);
   }
   float logit[kNCls];
-  ffn_forward(v, logit);
+  ffn_forward(w, v, logit);
   uint8_t lab = decide(logit);
   if (!ok) {
     logit[0] = logit[1] = logit[2] = NAN;
@@ -675,94 +757,242 @@ struct BankParams {
 };
 constexpr int kStreamFramePitch = 416;  // samples per staged frame row (208 words == 16 mod 32)
 constexpr int kStreamSmemBytes = kStepFrames * kStreamFramePitch * 2 + kWarps * 2 * kExchFrame * 8 +
-                                 kBins * kPPitch * 4 + kNMel * 32 * 4 + kNCep * 32 * 4 + 384 * 8;
+                                 kBins * kPPitch * 4 + kNMel * 32 * 4 + 384 * 8;
 
-__global__ void __launch_bounds__(kThreads) stream_feed_kernel(const BankParams p) {
+// One CTA = 32 streams.  FFT: the fused kernel's packed two-frames-per-thread pass.  The decision
+// tail is spread over all 8 warps with lane = stream: warp w owns cepstral coefficients w, w + 8
+// (DCT, ring push, window features) and then 8 / 4 / 2 neurons of layers 1 / 2 / 3, activations
+// handed over through shared memory (the idle P tile); weights are uniform constant-bank operands.
+__global__ void __launch_bounds__(kThreads) stream_feed_kernel(const BankParams p, const __grid_constant__ FfnParams w) {
   extern __shared__ __align__(128) unsigned char smem[];
   int16_t* s_fr = reinterpret_cast<int16_t*>(smem);
   cf2* s_exch = reinterpret_cast<cf2*>(smem + kStepFrames * kStreamFramePitch * 2);
   float* s_P = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_exch) + kWarps * 2 * kExchFrame * 8);
   float* s_logE = s_P + kBins * kPPitch;
-  float* s_mf = s_logE + kNMel * 32;
-  cf2* s_tw1 = reinterpret_cast<cf2*>(s_mf + kNCep * 32);
+  cf2* s_tw1 = reinterpret_cast<cf2*>(s_logE + kNMel * 32);
   cf2* s_tw2 = s_tw1 + 256;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, h = lane >> 4, t = lane & 15;
+  // after the mel phase the P tile is dead: activations live there
+  float* s_x = s_P;                    // [39][32]
+  float* s_h1 = s_x + kNFeat * 32;     // [64][32]
+  float* s_h2 = s_h1 + kH1 * 32;       // [32][32]
+  float* s_h3 = s_h2 + kH2 * 32;       // [16][32]
+  int* s_ok = reinterpret_cast<int*>(s_h3 + kH3 * 32);  // [13][32]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, h = lane >> 4;
   const int s0 = blockIdx.x * kStepFrames;
   s_tw1[tid] = p.tw1[tid];
   if (tid < 128) s_tw2[tid] = p.tw2[tid];
   // stage frames: [hist 320 | chunk 80] per stream, then roll the history in global memory
   for (int j = tid; j < kStepFrames * 200; j += kThreads) {  // 32-bit words: 160 hist + 40 chunk per stream
-    const int fi = j / 200, w = j - fi * 200;
+    const int fi = j / 200, wd = j - fi * 200;
     const int st = min(s0 + fi, p.n_streams - 1);
-    const uint32_t v = (w < 160) ? reinterpret_cast<const uint32_t*>(p.hist + static_cast<long long>(st) * 320)[w]
-                                 : reinterpret_cast<const uint32_t*>(p.chunks + static_cast<long long>(st) * 160)[w - 160];
-    reinterpret_cast<uint32_t*>(s_fr + fi * kStreamFramePitch)[w] = v;
+    const uint32_t v = (wd < 160) ? reinterpret_cast<const uint32_t*>(p.hist + static_cast<long long>(st) * 320)[wd]
+                                  : reinterpret_cast<const uint32_t*>(p.chunks + static_cast<long long>(st) * 160)[wd - 160];
+    reinterpret_cast<uint32_t*>(s_fr + fi * kStreamFramePitch)[wd] = v;
   }
   __syncthreads();
   // new history = old hist[160:320] ++ chunk[0:160]
   for (int j = tid; j < kStepFrames * 160; j += kThreads) {
-    const int fi = j / 160, w = j - fi * 160;
+    const int fi = j / 160, wd = j - fi * 160;
     const int st = s0 + fi;
     if (st < p.n_streams) {
-      const uint32_t v = (w < 80) ? reinterpret_cast<const uint32_t*>(s_fr + fi * kStreamFramePitch)[80 + w]
-                                  : reinterpret_cast<const uint32_t*>(p.chunks + static_cast<long long>(st) * 160)[w - 80];
-      reinterpret_cast<uint32_t*>(p.hist + static_cast<long long>(st) * 320)[w] = v;
+      const uint32_t v = (wd < 80) ? reinterpret_cast<const uint32_t*>(s_fr + fi * kStreamFramePitch)[80 + wd]
+                                   : reinterpret_cast<const uint32_t*>(p.chunks + static_cast<long long>(st) * 160)[wd - 80];
+      reinterpret_cast<uint32_t*>(p.hist + static_cast<long long>(st) * 320)[wd] = v;
     }
   }
-  cf2* ex = s_exch + (warp * 2 + h) * kExchFrame;
-#pragma unroll 1
-  for (int r = 0; r < 2; ++r) {
-    const int fi = warp * 4 + r * 2 + h;
-    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(s_fr + fi * kStreamFramePitch);
-    warp_fft_pair<13>([&](float (&xr)[16], float (&xi)[16]) { fft_load_pcm(w32, t, xr, xi); }, ex, s_tw1, s_tw2,
-                      s_P, fi, lane);
+  {
+    f2* ex = reinterpret_cast<f2*>(s_exch) + (warp * 2 + h) * kExchFrame;
+    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(s_fr + (warp * 4 + h) * kStreamFramePitch);
+    warp_fft_quad<13>(w32, kStreamFramePitch, ex, s_tw1, s_tw2, s_P, warp * 4 + 2 * h, lane);
   }
   __syncthreads();
   mel_group_dispatch<kPPitch, 32>(warp, s_P + lane, s_logE + lane);
   __syncthreads();
-  s_mf[warp * 32 + lane] = dct_coef<32>(s_logE + lane, warp);
-  if (warp + 8 < kNCep) s_mf[(warp + 8) * 32 + lane] = dct_coef<32>(s_logE + lane, warp + 8);
+  // ---- DCT + ring + window features: warp = coefficient (w, w + 8), lane = P column ----------------
+  const int slot = slot_of_col(lane);      // stream of this lane inside the CTA
+  const int st = s0 + slot;
+  const bool live = st < p.n_streams;
+  const long long ns = p.n_streams;
+  const int fed = live ? p.fed[st] : 0;    // chunks fed before this one
+  const int frame = fed - 2;               // index of the frame completed by this chunk (< 0: none yet)
+  const bool classify = frame >= 5;        // ring holds frames frame-5 .. frame-1: classify frame-3
+#pragma unroll
+  for (int rep = 0; rep < 2; ++rep) {
+    const int k = warp + 8 * rep;
+    if (k < kNCep) {                       // warp-uniform
+      const float cnew = dct_coef<32>(s_logE + lane, k);
+      float r[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      if (live && frame >= 0) {
+#pragma unroll
+        for (int d = 0; d < 5; ++d) r[d] = p.ring[(d * kNCep + k) * ns + st];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) p.ring[(d * kNCep + k) * ns + st] = r[d + 1];
+        p.ring[(4 * kNCep + k) * ns + st] = cnew;
+      }
+      float z = r[2];
+      bool ok = true;
+      if (p.feat_mode == 0) {
+        const float mu = ((((r[0] + r[1]) + r[2]) + r[3]) + r[4]) * 0.2f;
+        const float d0 = r[0] - mu, d1 = r[1] - mu, d2 = r[2] - mu, d3 = r[3] - mu, d4 = r[4] - mu;
+        const float var = fmaf(d4, d4, fmaf(d3, d3, fmaf(d2, d2, fmaf(d1, d1, d0 * d0)))) * 0.2f;
+        const bool alleq = (r[0] == r[1]) && (r[1] == r[2]) && (r[2] == r[3]) && (r[3] == r[4]);
+        z = alleq ? NAN : d2 * vadb_rsqrt(var);
+        ok = fabsf(z) <= 3.0e38f;
+      }
+      s_x[k * 32 + slot] = z;
+      s_x[(kNCep + k) * 32 + slot] = r[3] - r[1];
+      s_x[(2 * kNCep + k) * 32 + slot] = (r[4] - z) - (z - r[0]);
+      s_ok[k * 32 + slot] = ok ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  // ---- FFN, lane = stream (slot order from here on) --------------------------------------------------
+  {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = w.b1[8 * warp + j];
+#pragma unroll 3
+    for (int i = 0; i < kNFeat; ++i) {
+      const float xv = s_x[i * 32 + lane];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(xv, w.W1[i * kH1 + 8 * warp + j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_h1[(8 * warp + j) * 32 + lane] = fmaxf(acc[j], 0.0f);
+  }
+  __syncthreads();
+  {
+    float acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = w.b2[4 * warp + j];
+#pragma unroll 4
+    for (int i = 0; i < kH1; ++i) {
+      const float a = s_h1[i * 32 + lane];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(a, w.W2[i * kH2 + 4 * warp + j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s_h2[(4 * warp + j) * 32 + lane] = fmaxf(acc[j], 0.0f);
+  }
+  __syncthreads();
+  {
+    float acc[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) acc[j] = w.b3[2 * warp + j];
+#pragma unroll 4
+    for (int i = 0; i < kH2; ++i) {
+      const float a = s_h2[i * 32 + lane];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) acc[j] = fmaf(a, w.W3[i * kH3 + 2 * warp + j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) s_h3[(2 * warp + j) * 32 + lane] = fmaxf(acc[j], 0.0f);
+  }
   __syncthreads();
   if (warp == 0) {
-    const int st = s0 + lane;
-    if (st < p.n_streams) {
-      const int fed = p.fed[st];         // chunks fed before this one
-      const int frame = fed - 2;         // index of the frame completed by this chunk (< 0: none yet)
+    const int stl = s0 + lane;
+    if (stl < p.n_streams) {
+      const int fedl = p.fed[stl];
       uint8_t lab = 255;
       float lg[3] = {NAN, NAN, NAN};
-      float r[5][kNCep];
-      const long long ns = p.n_streams;
-      if (frame >= 0) {
+      if (fedl - 2 >= 5) {
+        float acc[kNCls];
 #pragma unroll
-        for (int d = 0; d < 5; ++d)
+        for (int o = 0; o < kNCls; ++o) acc[o] = w.b4[o];
 #pragma unroll
-          for (int k = 0; k < kNCep; ++k) r[d][k] = p.ring[(d * kNCep + k) * ns + st];
-        if (frame >= 5) {  // ring holds frames frame-5 .. frame-1: classify frame-3
-          float x[kNFeat];
-          const bool ok = window_features(r, p.feat_mode, x);
-          ffn_forward(x, lg);
-          lab = decide(lg);
-          if (!ok) {
-            lg[0] = lg[1] = lg[2] = NAN;
-            lab = 0;
-          }
+        for (int i = 0; i < kH3; ++i) {
+          const float a = s_h3[i * 32 + lane];
+#pragma unroll
+          for (int o = 0; o < kNCls; ++o) acc[o] = fmaf(a, w.W4[i * kNCls + o], acc[o]);
         }
-        // push: slots shift down by one, newest in slot 4
+        bool ok = true;
 #pragma unroll
-        for (int d = 0; d < 4; ++d)
-#pragma unroll
-          for (int k = 0; k < kNCep; ++k) p.ring[(d * kNCep + k) * ns + st] = r[d + 1][k];
-#pragma unroll
-        for (int k = 0; k < kNCep; ++k) p.ring[(4 * kNCep + k) * ns + st] = s_mf[k * 32 + lane];
+        for (int k = 0; k < kNCep; ++k) ok = ok && (s_ok[k * 32 + lane] != 0);
+        lab = decide(acc);
+        if (ok) {
+          lg[0] = acc[0]; lg[1] = acc[1]; lg[2] = acc[2];
+        } else {
+          lab = 0;
+        }
       }
-      p.fed[st] = fed + 1;
-      p.labels[st] = lab;
+      p.fed[stl] = fedl + 1;
+      p.labels[stl] = lab;
       if (p.logits) {
-        p.logits[st * 3 + 0] = lg[0];
-        p.logits[st * 3 + 1] = lg[1];
-        p.logits[st * 3 + 2] = lg[2];
+        p.logits[stl * 3 + 0] = lg[0];
+        p.logits[stl * 3 + 1] = lg[1];
+        p.logits[stl * 3 + 2] = lg[2];
       }
     }
+  }
+}
+
+// ---- feature sink: scale_features (dataset/utils.py:5-32) on packed dataset rows [n][39] ----------------
+// One scalar mean and one population standard deviation per group g in {mfcc, d1, d2} over all n x 13
+// values of the step, float64 accumulation like numpy.  Three passes over the rows:
+//   pass 0: acc[g] += sum v;   pass 1: acc[3 + g] += sum (v - mean_g)^2;   pass 2: v = (v - mean_g) / std_g.
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+__global__ void __launch_bounds__(256) scale_rows_kernel(float* rows, long long n_rows, int pass, double* acc) {
+  const long long total = n_rows * kNFeat;
+  const double cnt = static_cast<double>(n_rows) * kNCep;
+  double mean[3] = {0.0, 0.0, 0.0}, inv[3] = {0.0, 0.0, 0.0};
+  if (pass >= 1) {
+#pragma unroll
+    for (int g = 0; g < 3; ++g) mean[g] = acc[g] / cnt;
+  }
+  if (pass == 2) {
+#pragma unroll
+    for (int g = 0; g < 3; ++g) inv[g] = 1.0 / sqrt(acc[3 + g] / cnt);  // std == 0 -> inf -> nan rows, as numpy
+  }
+  double part[3] = {0.0, 0.0, 0.0};
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long j = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; j < total; j += stride) {
+    const int col = static_cast<int>(j % kNFeat);
+    const int g = col / kNCep;
+    const double v = static_cast<double>(rows[j]);
+    if (pass == 0) {
+      part[g] += v;
+    } else if (pass == 1) {
+      const double d = v - mean[g];
+      part[g] += d * d;
+    } else {
+      rows[j] = static_cast<float>((v - mean[g]) * inv[g]);
+    }
+  }
+  if (pass == 2) return;
+  __shared__ double s_part[3][8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int g = 0; g < 3; ++g) {
+    const double w = warp_sum(part[g]);
+    if (lane == 0) s_part[g][warp] = w;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_part[threadIdx.x][w];
+    atomicAdd(acc + 3 * pass + threadIdx.x, t);
+  }
+}
+
+// ---- ingest: 16-bit PCM byte streams -> packed int16 (dataset/sph.py:33-63 big-endian decode,
+// dataset/file_processing.py:87-94 STM segment concatenation) --------------------------------------------
+// Segment i copies len[i] samples starting at sample index src[i] of the raw stream (byte offset 2 src[i]
+// from raw) to dst[dst_off[i] ...]; big_endian swaps the two bytes of every sample (NIST SPHERE pcm).
+__global__ void __launch_bounds__(256) ingest_kernel(const uint8_t* raw, int big_endian, const long long* src,
+                                                     const long long* dst_off, const long long* len, int16_t* dst) {
+  const int seg = blockIdx.y;
+  const long long n = len[seg];
+  const uint16_t* in = reinterpret_cast<const uint16_t*>(raw) + src[seg];
+  int16_t* out = dst + dst_off[seg];
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long k = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; k < n; k += stride) {
+    uint16_t v = in[k];
+    if (big_endian) v = static_cast<uint16_t>((v << 8) | (v >> 8));
+    out[k] = static_cast<int16_t>(v);
   }
 }
 
@@ -802,7 +1032,7 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* sink, int iters, 
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         if (VARIANT == 0) acc[i] = fmaf(acc[i], m, a);
-        else acc[i] = fmaf(acc[i], c_par.W1[rep * 16 + i], a);
+        else acc[i] = fmaf(acc[i], c_tab.melw[rep * 16 + i], a);
       }
     }
   }

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -26,8 +27,8 @@ namespace {
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 std::atomic<unsigned long long> g_next_id{1};
-std::mutex g_const_mu;
-unsigned long long g_const_owner[64] = {0};  // per device: (handle id << 20) | version
+std::mutex g_tab_mu;
+bool g_tab_loaded[64] = {false};  // per device: mel / DCT tables uploaded (config-invariant content)
 
 int fail(int code, const std::string& msg) {
   g_err = msg;
@@ -45,6 +46,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 long long* g_dbg_ts = nullptr;  // timing experiments only (vadb200_debug_timestamps)
 constexpr int kNumSmFallback = 148;
+constexpr int kPlanCounters = 16;  // launches of one plan that may be in flight at once (any streams)
 constexpr int kHostBufs = 3;
 
 }  // namespace
@@ -55,7 +57,10 @@ struct vadb200_handle {
   unsigned version = 1;
   MfccConfig cfg;
   std::vector<double> fb;
-  ConstParams par;
+  MelDctTables tab;   // identical for every handle (only the reference configuration is compiled in)
+  FfnParams par;      // per-handle FFN weights: passed to kernels as a launch parameter
+  FfnBias bias;       // the same biases for the tensor-core variant
+  int plan_seg_frames = 0;  // 0 = automatic segment length (vadb200_set_plan_segment_frames)
   bool have_ffn = false;
   cf2* d_tw = nullptr;  // tw1[256] then tw2[128]
   int num_sms = kNumSmFallback;
@@ -67,7 +72,8 @@ struct vadb200_handle {
   int16_t* d_stage[kHostBufs] = {};
   uint8_t* d_lab[kHostBufs] = {};
   float* d_lgt[kHostBufs] = {};
-  long long stage_cap = 0, lab_cap = 0, lgt_cap = 0;
+  float* d_rows[kHostBufs] = {};
+  long long stage_cap = 0, lab_cap = 0, lgt_cap = 0, rows_cap = 0;
   float* d_sink = nullptr;
   unsigned char* d_tc_blob = nullptr;  // canonical tf32 hi/lo weight blob (ffn_tc.cuh)
   int ffn_impl = 1;                    // 0: FP32 CUDA cores, 1: tcgen05 tf32 x3 (default)
@@ -80,8 +86,10 @@ struct vadb200_plan {
   std::vector<long long> offsets, lengths, row_off, utt_seg;  // utt_seg: n_utt + 1
   std::vector<Segment> segs;
   Segment* d_segs = nullptr;
-  int* d_counter = nullptr;
+  int* d_counter = nullptr;   // kPlanCounters self-resetting (next segment, CTAs done) pairs
+  std::atomic<unsigned> launch_seq{0};
   long long total_rows = 0;
+  long long seg_frames = 0;
 };
 
 struct vadb200_bank {
@@ -94,18 +102,16 @@ struct vadb200_bank {
 
 namespace {
 
-// Upload the handle's constant block if another handle (or an older version) owns the bank.
-// Ownership changes are rare (new handle / new weights), so they are made fully synchronous:
-// drain every stream that may still read the old constants, then copy with the blocking call,
-// so launches on ANY stream afterwards see the new block.
-int ensure_constants(vadb200_handle* h, cudaStream_t) {
-  std::lock_guard<std::mutex> lk(g_const_mu);
-  const unsigned long long tag = (h->id << 20) | h->version;
-  if (h->device < 64 && g_const_owner[h->device] == tag) return 0;
+// Mel weights and the folded DCT matrix are the same for every handle (the kernels are compiled for the
+// reference configuration only), so the __constant__ copy is written once per device and never changes:
+// no handle can observe another handle's state through it.  FFN weights never go through device globals.
+int ensure_tables(vadb200_handle* h) {
+  if (h->device >= 64) return fail(VADB200_E_INVALID, "device index >= 64");
+  std::lock_guard<std::mutex> lk(g_tab_mu);
+  if (g_tab_loaded[h->device]) return 0;
+  CU(cudaMemcpyToSymbol(c_tab, &h->tab, sizeof(MelDctTables), 0, cudaMemcpyHostToDevice));
   CU(cudaDeviceSynchronize());
-  CU(cudaMemcpyToSymbol(c_par, &h->par, sizeof(ConstParams), 0, cudaMemcpyHostToDevice));
-  CU(cudaDeviceSynchronize());
-  if (h->device < 64) g_const_owner[h->device] = tag;
+  g_tab_loaded[h->device] = true;
   return 0;
 }
 
@@ -127,9 +133,10 @@ int launch_fused(vadb200_plan* p, FusedParams fp, int n_segs, cudaStream_t st) {
   if (n_segs <= 0) return 0;
   int rc = ensure_attrs(h);
   if (rc) return rc;
-  rc = ensure_constants(h, st);
+  rc = ensure_tables(h);
   if (rc) return rc;
-  CU(cudaMemsetAsync(p->d_counter, 0, sizeof(int), st));
+  // each launch takes its own self-resetting counter pair, so one plan can be in flight on several streams
+  fp.counter = p->d_counter + 2 * (p->launch_seq.fetch_add(1) % kPlanCounters);
 #if defined(VADB_DEBUG_HOOKS)
   const char* gps = std::getenv("VADB200_CTAS_PER_SM");  // occupancy experiments only
   const int per_sm = gps ? std::max(1, std::atoi(gps)) : 2;
@@ -138,11 +145,11 @@ int launch_fused(vadb200_plan* p, FusedParams fp, int n_segs, cudaStream_t st) {
 #endif
   const int grid = std::min(n_segs, per_sm * h->num_sms);
   switch (p->mode) {
-    case VADB200_MODE_MFCC: fused_kernel<0, 0><<<grid, kThreads, kFusedSmemBytes, st>>>(fp); break;
-    case VADB200_MODE_DATASET: fused_kernel<1, 0><<<grid, kThreads, kFusedSmemBytes, st>>>(fp); break;
+    case VADB200_MODE_MFCC: fused_kernel<0, 0><<<grid, kThreads, kFusedSmemBytes, st>>>(fp, FfnNone{0}); break;
+    case VADB200_MODE_DATASET: fused_kernel<1, 0><<<grid, kThreads, kFusedSmemBytes, st>>>(fp, FfnNone{0}); break;
     default:
-      if (h->ffn_impl == 1) fused_kernel<2, 1><<<grid, kThreads, kFusedSmemBytes, st>>>(fp);
-      else fused_kernel<2, 0><<<grid, kThreads, kFusedSmemBytes, st>>>(fp);
+      if (h->ffn_impl == 1) fused_kernel<2, 1><<<grid, kThreads, kFusedSmemBytes, st>>>(fp, h->bias);
+      else fused_kernel<2, 0><<<grid, kThreads, kFusedSmemBytes, st>>>(fp, h->par);
       break;
   }
   g_launches.fetch_add(1);
@@ -154,7 +161,7 @@ FusedParams base_params(vadb200_plan* p) {
   FusedParams fp;
   std::memset(&fp, 0, sizeof(fp));
   fp.segs = p->d_segs;
-  fp.counter = p->d_counter;
+  fp.counter = p->d_counter;  // launch_fused picks the launch's own pair
   fp.tw1 = p->h->d_tw;
   fp.tw2 = p->h->d_tw + 256;
   fp.tc_blob = p->h->d_tc_blob;
@@ -221,13 +228,15 @@ int vadb200_create(const vadb200_config* c, int device, vadb200_handle** out) {
   h->cfg = cfg;
   h->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : kNumSmFallback;
   h->fb = mel_filterbank(cfg);
-  std::memset(&h->par, 0, sizeof(ConstParams));
+  std::memset(&h->par, 0, sizeof(FfnParams));
+  std::memset(&h->bias, 0, sizeof(FfnBias));
+  std::memset(&h->tab, 0, sizeof(MelDctTables));
   std::string why;
-  if (!pack_mel_weights(h->fb.data(), h->par.melw, &why)) {
+  if (!pack_mel_weights(h->fb.data(), h->tab.melw, &why)) {
     delete h;
     return fail(VADB200_E_UNSUPPORTED, why);
   }
-  folded_dct(cfg, h->par.dct);
+  folded_dct(cfg, h->tab.dct);
   cf2 tw[384];
   fft_twiddles(tw, tw + 256);
   cudaError_t e = cudaMalloc(&h->d_tw, sizeof(tw));
@@ -240,6 +249,16 @@ int vadb200_create(const vadb200_config* c, int device, vadb200_handle** out) {
     delete h;
     return cuda_fail(e, "vadb200_create");
   }
+  // function attributes and the (config-invariant) constant tables now, so that no launch ever
+  // synchronises: every device-pointer entry point can be captured into a CUDA graph
+  int rc = ensure_attrs(h);
+  if (!rc) rc = ensure_tables(h);
+  if (rc) {
+    const std::string keep = g_err;
+    vadb200_destroy(h);
+    g_err = keep;
+    return rc;
+  }
   *out = h;
   return 0;
 }
@@ -248,7 +267,7 @@ int vadb200_destroy(vadb200_handle* h) {
   if (!h) return 0;
   cudaSetDevice(h->device);
   for (int i = 0; i < kHostBufs; ++i) {
-    cudaFree(h->d_stage[i]); cudaFree(h->d_lab[i]); cudaFree(h->d_lgt[i]);
+    cudaFree(h->d_stage[i]); cudaFree(h->d_lab[i]); cudaFree(h->d_lgt[i]); cudaFree(h->d_rows[i]);
     if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
     if (h->ev_done[i]) cudaEventDestroy(h->ev_done[i]);
     if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
@@ -276,6 +295,8 @@ int vadb200_set_ffn_weights(vadb200_handle* h, const float* W1, const float* b1,
   std::memcpy(h->par.W2, W2, sizeof(h->par.W2)); std::memcpy(h->par.b2, b2, sizeof(h->par.b2));
   std::memcpy(h->par.W3, W3, sizeof(h->par.W3)); std::memcpy(h->par.b3, b3, sizeof(h->par.b3));
   std::memcpy(h->par.W4, W4, sizeof(h->par.W4)); std::memcpy(h->par.b4, b4, sizeof(h->par.b4));
+  std::memcpy(h->bias.b1, b1, sizeof(h->bias.b1)); std::memcpy(h->bias.b2, b2, sizeof(h->bias.b2));
+  std::memcpy(h->bias.b3, b3, sizeof(h->bias.b3)); std::memcpy(h->bias.b4, b4, sizeof(h->bias.b4));
   h->have_ffn = true;
   h->version = (h->version + 1) & 0xFFFFF;
   // tensor-core operand blob; drained + blocking so kernels on any stream see a consistent copy
@@ -328,8 +349,14 @@ int vadb200_plan_create(vadb200_handle* h, const int64_t* offs, const int64_t* l
   // Segment length: long runs amortise the 4-frame halo; short ones keep all CTAs busy on small
   // batches.  n_frames of a full segment is a multiple of 32 (whole steps).
   const int halo = (mode == VADB200_MODE_MFCC) ? 0 : 4;
-  long long want = (rows + 4ll * 2 * h->num_sms - 1) / (4ll * 2 * h->num_sms);
-  long long seg_frames = std::min<long long>(2048, std::max<long long>(64, ((want + halo + 31) / 32) * 32));
+  long long seg_frames = h->plan_seg_frames;
+  if (seg_frames <= 0) {
+    // >= 16 segments per persistent CTA when the batch allows (dynamic scheduling then balances to a few
+    // per cent), whole 128-frame tensor-core tiles, at most 2048 frames
+    const long long want = rows / (16ll * 2 * h->num_sms) + halo;
+    seg_frames = want <= 64 ? 64 : std::min<long long>(2048, ((want + 127) / 128) * 128);
+  }
+  p->seg_frames = seg_frames;
   const long long seg_rows = seg_frames - halo;
   for (long long u = 0; u < n_utt; ++u) {
     p->utt_seg[u] = static_cast<long long>(p->segs.size());
@@ -349,7 +376,8 @@ int vadb200_plan_create(vadb200_handle* h, const int64_t* offs, const int64_t* l
     return fail(VADB200_E_INVALID, "too many segments");
   }
   cudaError_t e = cudaSetDevice(h->device);
-  if (e == cudaSuccess) e = cudaMalloc(&p->d_counter, sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&p->d_counter, 2 * kPlanCounters * sizeof(int));
+  if (e == cudaSuccess) e = cudaMemset(p->d_counter, 0, 2 * kPlanCounters * sizeof(int));
   if (e == cudaSuccess && !p->segs.empty()) {
     e = cudaMalloc(&p->d_segs, p->segs.size() * sizeof(Segment));
     if (e == cudaSuccess)
@@ -374,6 +402,15 @@ int vadb200_plan_destroy(vadb200_plan* p) {
 }
 
 int64_t vadb200_plan_total_rows(const vadb200_plan* p) { return p ? p->total_rows : -1; }
+int64_t vadb200_plan_segment_frames(const vadb200_plan* p) { return p ? p->seg_frames : -1; }
+int64_t vadb200_plan_segment_count(const vadb200_plan* p) { return p ? static_cast<int64_t>(p->segs.size()) : -1; }
+
+int vadb200_set_plan_segment_frames(vadb200_handle* h, int frames) {
+  if (!h || frames < 0 || frames > 2048 || (frames != 0 && (frames < 64 || frames % 32)))
+    return fail(VADB200_E_INVALID, "segment length must be 0 (automatic) or a multiple of 32 in [64, 2048]");
+  h->plan_seg_frames = frames;
+  return 0;
+}
 
 int vadb200_plan_row_offsets(const vadb200_plan* p, int64_t* out) {
   if (!p || !out) return fail(VADB200_E_INVALID, "null argument");
@@ -419,7 +456,8 @@ int vadb200_vad_packed(vadb200_plan* p, const int16_t* d_pcm, int64_t pcm_len, u
 }
 
 // ---- host-buffer pipeline ---------------------------------------------------------------------------------
-static int ensure_host_pipeline(vadb200_handle* h, long long stage_samples, long long rows, bool want_logits) {
+static int ensure_host_pipeline(vadb200_handle* h, long long stage_samples, long long rows, bool want_labels,
+                                bool want_logits, long long row_floats) {
   if (!h->s_in) {
     CU(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&h->s_run, cudaStreamNonBlocking));
@@ -437,7 +475,7 @@ static int ensure_host_pipeline(vadb200_handle* h, long long stage_samples, long
     }
     h->stage_cap = stage_samples;
   }
-  if (rows > h->lab_cap) {
+  if (want_labels && rows > h->lab_cap) {
     for (int i = 0; i < kHostBufs; ++i) {
       cudaFree(h->d_lab[i]); h->d_lab[i] = nullptr;
       CU(cudaMalloc(&h->d_lab[i], rows));
@@ -451,20 +489,26 @@ static int ensure_host_pipeline(vadb200_handle* h, long long stage_samples, long
     }
     h->lgt_cap = rows;
   }
+  if (row_floats > h->rows_cap) {
+    for (int i = 0; i < kHostBufs; ++i) {
+      cudaFree(h->d_rows[i]); h->d_rows[i] = nullptr;
+      CU(cudaMalloc(&h->d_rows[i], row_floats * sizeof(float)));
+    }
+    h->rows_cap = row_floats;
+  }
   return 0;
 }
 
-int vadb200_vad_host(vadb200_plan* p, const int16_t* h_pcm, int64_t pcm_len, uint8_t* h_labels, float* h_logits,
-                     int feat_mode) {
-  if (!p) return fail(VADB200_E_INVALID, "plan is null");
-  if (p->mode != VADB200_MODE_VAD) return fail(VADB200_E_INVALID, "plan was not created for MODE_VAD");
+// Chunked H2D -> fused kernel -> D2H over three staging buffers and three streams.  VAD plans return
+// labels (+ logits); MFCC / dataset plans return float rows of `width` columns.
+static int run_host_pipeline(vadb200_plan* p, const int16_t* h_pcm, int64_t pcm_len, uint8_t* h_labels, float* h_logits,
+                             float* h_rows, int feat_mode) {
   vadb200_handle* h = p->h;
-  if (!h->have_ffn) return fail(VADB200_E_STATE, "FFN weights not set (vadb200_set_ffn_weights)");
   if (p->total_rows == 0) return 0;
-  if (!h_pcm || !h_labels) return fail(VADB200_E_INVALID, "null argument");
   if (p->n_utt > 0 && pcm_len < p->offsets[p->n_utt - 1] + p->lengths[p->n_utt - 1])
     return fail(VADB200_E_INVALID, "pcm_len is smaller than the last utterance's end");
   CU(cudaSetDevice(h->device));
+  const long long width = p->mode == VADB200_MODE_VAD ? 0 : (p->mode == VADB200_MODE_MFCC ? kNCep : kNFeat);
   // chunks = runs of whole utterances whose PCM span fits host_chunk_samples
   struct Chunk { long long u0, u1, s0, s1; };
   std::vector<Chunk> chunks;
@@ -478,7 +522,9 @@ int vadb200_vad_host(vadb200_plan* p, const int16_t* h_pcm, int64_t pcm_len, uin
     chunks.push_back(c);
     u = c.u1;
   }
-  int rc = ensure_host_pipeline(h, ((max_span + 7) & ~7ll) + 8, std::max<long long>(max_rows, 1), h_logits != nullptr);
+  max_rows = std::max<long long>(max_rows, 1);
+  int rc = ensure_host_pipeline(h, ((max_span + 7) & ~7ll) + 8, max_rows, h_labels != nullptr, h_logits != nullptr,
+                                width * max_rows);
   if (rc) return rc;
   for (size_t i = 0; i < chunks.size(); ++i) {
     const Chunk& c = chunks[i];
@@ -489,12 +535,13 @@ int vadb200_vad_host(vadb200_plan* p, const int16_t* h_pcm, int64_t pcm_len, uin
     CU(cudaMemcpyAsync(h->d_stage[b], h_pcm + c.s0, span * sizeof(int16_t), cudaMemcpyHostToDevice, h->s_in));
     CU(cudaEventRecord(h->ev_in[b], h->s_in));
     CU(cudaStreamWaitEvent(h->s_run, h->ev_in[b], 0));
-    if (i >= kHostBufs) CU(cudaStreamWaitEvent(h->s_run, h->ev_out[b], 0));  // label buffer drained
+    if (i >= kHostBufs) CU(cudaStreamWaitEvent(h->s_run, h->ev_out[b], 0));  // result buffers drained
     FusedParams fp = base_params(p);
     fp.pcm = h->d_stage[b] - c.s0;  // segment sample indices stay absolute
     fp.pcm_len = c.s1;
-    fp.labels = h->d_lab[b];
+    fp.labels = h_labels ? h->d_lab[b] : nullptr;
     fp.logits = h_logits ? h->d_lgt[b] : nullptr;
+    fp.rows = width ? h->d_rows[b] : nullptr;
     fp.row_base = r0;
     fp.feat_mode = feat_mode;
     fp.seg_begin = static_cast<int>(p->utt_seg[c.u0]);
@@ -504,14 +551,86 @@ int vadb200_vad_host(vadb200_plan* p, const int16_t* h_pcm, int64_t pcm_len, uin
     CU(cudaEventRecord(h->ev_done[b], h->s_run));
     CU(cudaStreamWaitEvent(h->s_out, h->ev_done[b], 0));
     if (nrows > 0) {
-      CU(cudaMemcpyAsync(h_labels + r0, h->d_lab[b], nrows, cudaMemcpyDeviceToHost, h->s_out));
+      if (h_labels) CU(cudaMemcpyAsync(h_labels + r0, h->d_lab[b], nrows, cudaMemcpyDeviceToHost, h->s_out));
       if (h_logits)
         CU(cudaMemcpyAsync(h_logits + r0 * 3, h->d_lgt[b], nrows * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->s_out));
+      if (width)
+        CU(cudaMemcpyAsync(h_rows + r0 * width, h->d_rows[b], nrows * width * sizeof(float), cudaMemcpyDeviceToHost,
+                           h->s_out));
     }
     CU(cudaEventRecord(h->ev_out[b], h->s_out));
   }
   CU(cudaStreamSynchronize(h->s_out));
   CU(cudaStreamSynchronize(h->s_run));
+  return 0;
+}
+
+int vadb200_vad_host(vadb200_plan* p, const int16_t* h_pcm, int64_t pcm_len, uint8_t* h_labels, float* h_logits,
+                     int feat_mode) {
+  if (!p) return fail(VADB200_E_INVALID, "plan is null");
+  if (p->mode != VADB200_MODE_VAD) return fail(VADB200_E_INVALID, "plan was not created for MODE_VAD");
+  if (!p->h->have_ffn) return fail(VADB200_E_STATE, "FFN weights not set (vadb200_set_ffn_weights)");
+  if (feat_mode != VADB200_FEAT_ANALYSER && feat_mode != VADB200_FEAT_DATASET) return fail(VADB200_E_INVALID, "unknown feat_mode");
+  if (p->total_rows == 0) return 0;
+  if (!h_pcm || !h_labels) return fail(VADB200_E_INVALID, "null argument");
+  return run_host_pipeline(p, h_pcm, pcm_len, h_labels, h_logits, nullptr, feat_mode);
+}
+
+int vadb200_mfcc_host(vadb200_plan* p, const int16_t* h_pcm, int64_t pcm_len, float* h_out) {
+  if (!p) return fail(VADB200_E_INVALID, "plan is null");
+  if (p->mode == VADB200_MODE_VAD) return fail(VADB200_E_INVALID, "plan was created for MODE_VAD");
+  if (p->total_rows == 0) return 0;
+  if (!h_pcm || !h_out) return fail(VADB200_E_INVALID, "null argument");
+  return run_host_pipeline(p, h_pcm, pcm_len, nullptr, nullptr, h_out, 0);
+}
+
+// ---- feature sink / ingest -------------------------------------------------------------------------------
+int vadb200_scale_rows(vadb200_handle* h, float* d_rows, int64_t n_rows, double* h_stats, void* stream) {
+  if (!h || n_rows < 0) return fail(VADB200_E_INVALID, "bad argument");
+  if (n_rows == 0) return 0;
+  if (!d_rows) return fail(VADB200_E_INVALID, "d_rows is null");
+  CU(cudaSetDevice(h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* acc = nullptr;
+  CU(cudaMallocAsync(&acc, 6 * sizeof(double), st));  // stream-ordered scratch: no per-handle state
+  CU(cudaMemsetAsync(acc, 0, 6 * sizeof(double), st));
+  const long long total = n_rows * kNFeat;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 8ll * h->num_sms));
+  for (int pass = 0; pass < 3; ++pass) {
+    scale_rows_kernel<<<grid, 256, 0, st>>>(d_rows, n_rows, pass, acc);
+    g_launches.fetch_add(1);
+  }
+  CU(cudaGetLastError());
+  if (h_stats) {
+    double raw[6];
+    CU(cudaMemcpyAsync(raw, acc, sizeof(raw), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    const double cnt = static_cast<double>(n_rows) * kNCep;
+    for (int g = 0; g < 3; ++g) {
+      h_stats[g] = raw[g] / cnt;
+      h_stats[3 + g] = std::sqrt(raw[3 + g] / cnt);
+    }
+  }
+  CU(cudaFreeAsync(acc, st));
+  return 0;
+}
+
+int vadb200_ingest_pcm(vadb200_handle* h, const void* d_raw, int big_endian, const int64_t* d_src_start,
+                       const int64_t* d_dst_start, const int64_t* d_len, int n_seg, int64_t max_len, int16_t* d_dst,
+                       void* stream) {
+  if (!h || n_seg < 0 || max_len < 0) return fail(VADB200_E_INVALID, "bad argument");
+  if (n_seg == 0 || max_len == 0) return 0;
+  if (!d_raw || !d_src_start || !d_dst_start || !d_len || !d_dst) return fail(VADB200_E_INVALID, "null argument");
+  if (reinterpret_cast<uintptr_t>(d_raw) & 1) return fail(VADB200_E_INVALID, "raw sample stream must be 2-byte aligned");
+  if (n_seg > 65535) return fail(VADB200_E_INVALID, "at most 65535 segments per call");
+  CU(cudaSetDevice(h->device));
+  const unsigned gx = static_cast<unsigned>(std::min<long long>((max_len + 255) / 256, 4ll * h->num_sms));
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64_t layout");
+  ingest_kernel<<<dim3(gx, static_cast<unsigned>(n_seg)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint8_t*>(d_raw), big_endian, reinterpret_cast<const long long*>(d_src_start),
+      reinterpret_cast<const long long*>(d_dst_start), reinterpret_cast<const long long*>(d_len), d_dst);
+  g_launches.fetch_add(1);
+  CU(cudaGetLastError());
   return 0;
 }
 
@@ -526,7 +645,7 @@ static int frames_common(vadb200_handle* h, const float* d_frames, int64_t n, in
   int rc = ensure_attrs(h);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  rc = ensure_constants(h, st);
+  rc = ensure_tables(h);
   if (rc) return rc;
   const unsigned grid = static_cast<unsigned>((n + kStepFrames - 1) / kStepFrames);
   frames_kernel<<<grid, kThreads, kFramesSmemBytes, st>>>(d_frames, n, frame_len, what, d_out, h->d_tw, h->d_tw + 256);
@@ -549,7 +668,7 @@ int vadb200_mfcc_from_spec(vadb200_handle* h, const float* d_spec, int64_t n, fl
   if (!d_spec || !d_mfcc) return fail(VADB200_E_INVALID, "null argument");
   CU(cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = ensure_constants(h, st);
+  int rc = ensure_tables(h);
   if (rc) return rc;
   const unsigned grid = static_cast<unsigned>((n + kStepFrames - 1) / kStepFrames);
   spec_to_mfcc_kernel<<<grid, kThreads, 0, st>>>(d_spec, n, d_mfcc);
@@ -567,9 +686,10 @@ int vadb200_vad_windows(vadb200_handle* h, const float* d_win, int64_t n, int fe
   if (!d_win) return fail(VADB200_E_INVALID, "null argument");
   CU(cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = ensure_constants(h, st);
+  int rc = ensure_tables(h);
   if (rc) return rc;
-  windows_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(d_win, n, feat_mode, d_labels, d_logits, d_feats);
+  windows_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(d_win, n, feat_mode, d_labels, d_logits, d_feats,
+                                                                       h->par);
   g_launches.fetch_add(1);
   CU(cudaGetLastError());
   return 0;
@@ -583,15 +703,15 @@ int vadb200_ffn_predict(vadb200_handle* h, const float* d_x, int64_t n, uint8_t*
   if (!d_x) return fail(VADB200_E_INVALID, "null argument");
   CU(cudaSetDevice(h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int rc = ensure_constants(h, st);
+  int rc = ensure_tables(h);
   if (rc) return rc;
   if (h->ffn_impl == 1) {
     rc = ensure_attrs(h);
     if (rc) return rc;
     ffn_tc_rows_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, kFfnTcSmemBytes, st>>>(d_x, n, h->d_tc_blob,
-                                                                                                 d_labels, d_logits);
+                                                                                                 d_labels, d_logits, h->bias);
   } else {
-    ffn_rows_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(d_x, n, d_labels, d_logits);
+    ffn_rows_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(d_x, n, d_labels, d_logits, h->par);
   }
   g_launches.fetch_add(1);
   CU(cudaGetLastError());
@@ -671,13 +791,13 @@ int vadb200_stream_feed(vadb200_bank* b, const int16_t* d_chunks, uint8_t* d_lab
   int rc = ensure_attrs(h);
   if (rc) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  rc = ensure_constants(h, st);
+  rc = ensure_tables(h);
   if (rc) return rc;
   BankParams bp;
   bp.n_streams = b->n; bp.hist = b->d_hist; bp.ring = b->d_ring; bp.fed = b->d_fed;
   bp.chunks = d_chunks; bp.labels = d_labels; bp.logits = d_logits;
   bp.tw1 = h->d_tw; bp.tw2 = h->d_tw + 256; bp.feat_mode = VADB200_FEAT_ANALYSER;
-  stream_feed_kernel<<<(b->n + kStepFrames - 1) / kStepFrames, kThreads, kStreamSmemBytes, st>>>(bp);
+  stream_feed_kernel<<<(b->n + kStepFrames - 1) / kStepFrames, kThreads, kStreamSmemBytes, st>>>(bp, h->par);
   g_launches.fetch_add(1);
   CU(cudaGetLastError());
   return 0;
@@ -691,7 +811,7 @@ int vadb200_exp_fft(vadb200_plan* p, const int16_t* d_pcm, int64_t pcm_len, int 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   FusedParams fp = base_params(p);
   fp.pcm = d_pcm; fp.pcm_len = pcm_len; fp.seg_begin = 0; fp.seg_end = static_cast<int>(p->segs.size());
-  CU(cudaMemsetAsync(p->d_counter, 0, sizeof(int), st));
+  fp.counter = p->d_counter + 2 * (p->launch_seq.fetch_add(1) % kPlanCounters);
   const int grid = std::min<int>(fp.seg_end, minb * h->num_sms);
 #define VADB_EXP(M)                                                                                          \
   {                                                                                                          \
@@ -722,7 +842,7 @@ int vadb200_synth_pcm(vadb200_handle* h, int16_t* d_out, int64_t n_utt, int64_t 
 int vadb200_fp32_peak(vadb200_handle* h, int variant, int iters, double* tflops_out) {
   if (!h || !tflops_out || iters < 1 || variant < 0 || variant > 1) return fail(VADB200_E_INVALID, "bad argument");
   CU(cudaSetDevice(h->device));
-  int rc = ensure_constants(h, nullptr);
+  int rc = ensure_tables(h);
   if (rc) return rc;
   cudaEvent_t e0, e1;
   CU(cudaEventCreate(&e0));

@@ -177,6 +177,36 @@ class Handle(object):
     def set_host_chunk_samples(self, samples):
         check(self.lib.vadb200_set_host_chunk_samples(self._h, int(samples)))
 
+    def set_plan_segment_frames(self, frames):
+        """Override the segment length of plans created afterwards (0 = automatic)."""
+        check(self.lib.vadb200_set_plan_segment_frames(self._h, int(frames)))
+
+    # ---- feature sink / ingest ------------------------------------------------------------------
+    def scale_rows(self, rows, want_stats=True):
+        """dataset/utils.py:5-32 on a packed [n, 39] float32 CUDA tensor, in place.  Returns the six
+        statistics (mean x3, population std x3) as a float64 array when want_stats."""
+        if not (torch.is_tensor(rows) and rows.is_cuda and rows.dtype == torch.float32 and rows.is_contiguous()
+                and rows.dim() == 2 and rows.shape[1] == 39):
+            raise TypeError("rows must be a contiguous [n, 39] float32 CUDA tensor")
+        stats = np.zeros(6, dtype=np.float64) if want_stats else None
+        check(self.lib.vadb200_scale_rows(self._h, _ptr(rows), rows.shape[0],
+                                          stats.ctypes.data_as(C.c_void_p) if want_stats else C.c_void_p(0),
+                                          self.stream))
+        return stats
+
+    def ingest_pcm(self, raw, src_start, dst_start, lengths, out, big_endian=False):
+        """Device decode + gather: ``raw`` uint8 CUDA tensor holding 16-bit samples (2-byte aligned),
+        segment i = ``lengths[i]`` samples from sample index ``src_start[i]`` to ``out[dst_start[i]:]``."""
+        src = torch.as_tensor(np.asarray(src_start, dtype=np.int64)).to(self.device)
+        dst = torch.as_tensor(np.asarray(dst_start, dtype=np.int64)).to(self.device)
+        ln_host = np.asarray(lengths, dtype=np.int64)
+        ln = torch.as_tensor(ln_host).to(self.device)
+        if ln_host.size == 0:
+            return out
+        check(self.lib.vadb200_ingest_pcm(self._h, _ptr(raw), 1 if big_endian else 0, _ptr(src), _ptr(dst), _ptr(ln),
+                                          int(ln_host.size), int(ln_host.max()), _ptr(out), self.stream))
+        return out
+
 
 class Plan(object):
     """Segment table for one ragged packed batch (offsets / lengths in samples, host side)."""
@@ -195,6 +225,8 @@ class Plan(object):
                                            self.lengths.ctypes.data_as(C.c_void_p), self.n_utt, mode,
                                            C.byref(self._p)))
         self.total_rows = int(self.lib.vadb200_plan_total_rows(self._p))
+        self.segment_frames = int(self.lib.vadb200_plan_segment_frames(self._p))
+        self.segment_count = int(self.lib.vadb200_plan_segment_count(self._p))
         self.row_offsets = np.empty(self.n_utt + 1, dtype=np.int64)
         check(self.lib.vadb200_plan_row_offsets(self._p, self.row_offsets.ctypes.data_as(C.c_void_p)))
 
@@ -233,6 +265,16 @@ class Plan(object):
         check(self.lib.vadb200_vad_packed(self._p, _ptr(pcm), pcm.numel(), _ptr(labels), _ptr(logits), _ptr(feats),
                                           feat_mode, self.handle.stream))
         return labels, logits, feats
+
+    def mfcc_host(self, pcm_host, out_host=None):
+        """MODE_MFCC / MODE_DATASET end to end with HOST tensors: chunked H2D, fused kernel, D2H of the rows."""
+        if not (torch.is_tensor(pcm_host) and pcm_host.dtype == torch.int16 and not pcm_host.is_cuda):
+            raise TypeError("pcm_host must be a CPU torch.int16 tensor")
+        width = 13 if self.mode == MODE_MFCC else 39
+        if out_host is None:
+            out_host = torch.empty((self.total_rows, width), dtype=torch.float32).pin_memory()
+        check(self.lib.vadb200_mfcc_host(self._p, _ptr(pcm_host), pcm_host.numel(), _ptr(out_host)))
+        return out_host
 
     def vad_host(self, pcm_host, labels_host=None, logits_host=None, feat_mode=FEAT_ANALYSER):
         """End to end with HOST tensors (pinned for full PCIe speed): H2D, fused kernel, D2H."""
