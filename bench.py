@@ -32,6 +32,7 @@ if ROOT not in sys.path:
 METRIC = "audio_seconds_per_second"
 UNIT = "audio-s/s"
 FLOP_PER_FRAME_FUSED = 24663   # FFT 11520 + power 768 + mel 888 + log 26 + DCT 676 + window 340 + FFN 10208 + 237
+FLOP_PER_FRAME_MFCC = 13878    # MFCC-only subtotal (cfg2); dataset rows add 39 (cfg5)
 BYTES_PER_FRAME_FUSED = 321    # 160 int16 in + 1 label out
 FP32_NOMINAL_TFLOPS = 74.4     # 148 SM x 128 lanes x 2 x 1.965 GHz (fallback denominator)
 # dram__bytes_read.sum + dram__bytes_write.sum of fused_kernel<2,1> from the committed `ncu --set full`
@@ -52,9 +53,14 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-utts-per-core", type=int, default=16)
-    ap.add_argument("--ffn-impl", default="tc", choices=["tc", "fp32"],
-                    help="FFN contraction: tcgen05 tensor cores (tf32 x3) or FP32 CUDA cores")
+    ap.add_argument("--ffn-impl", default="tc16", choices=["tc16", "tc", "fp32"],
+                    help="FFN contraction: tcgen05 on fp16 hi/lo operands (default), tcgen05 on tf32 hi/lo operands, "
+                         "or FP32 CUDA cores")
     ap.add_argument("--seed", type=int, default=1234)
+    ap.add_argument("--stream-ticks", type=int, default=10000)
+    ap.add_argument("--streams", type=int, default=4096)
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the cfg2 / cfg4 / cfg5 sub-records")
+    ap.add_argument("--parity-utts", type=int, default=4)
     return ap.parse_args()
 
 
@@ -124,10 +130,18 @@ def run_cpu_port(utts, procs, steps, warmup, utt_seconds, seed):
     return json.loads(out.stdout.strip().splitlines()[-1])
 
 
+CPU_KIND_NOTE = {
+    "reference": "; UNMODIFIED reference process_file (wav read, framing, per-frame mfcc.get_mfcc, ring, deltas) from "
+                 "oracle/_ref through the python-3 shim + the oracle's vectorised classifier stage (the reference never "
+                 "runs its FFN)",
+    "port": "; oracle/ref_loop.py per-frame port (oracle/_ref not staged on this box)",
+}
+
+
 def reference_arm(a):
-    """The reference's own CPU implementation of the path.  /root/reference is pure Python 2 and
-    cannot travel to the GPU box, so the line-for-line port oracle/ref_loop.py stands in
-    (cpu_baseline.kind = "port"), on all host cores with the reference's Pool.map shape."""
+    """The reference's own CPU implementation of the path on all host cores with its Pool.map shape
+    (dataset_creator.py:63-65): the unmodified sources staged under oracle/_ref (kind "reference"), or the
+    per-frame port oracle/ref_loop.py where they are absent (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -136,12 +150,14 @@ def reference_arm(a):
     r = run_cpu_port(utts, cores, a.steps, a.warmup, a.utt_seconds, a.seed)
     sample = "%d x %.0f s synthetic utterances per step (%.0f audio-s), Pool(%d)" % (utts, a.utt_seconds,
                                                                                      utts * a.utt_seconds, cores)
+    kind = r.get("kind", "port")
     line = {
         "impl": "reference", "metric": METRIC, "value": r["audio_s_per_s"], "unit": UNIT, "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(a, a.gpus, sample_note="bounded sample per step: " + sample),
-        "cpu_baseline": {"value": r["audio_s_per_s"], "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": r["audio_s_per_s"], "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": sample + CPU_KIND_NOTE[kind]},
         "e2e": {"value": r["audio_s_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -304,11 +320,14 @@ def main():
     achieved = frames * FLOP_PER_FRAME_FUSED / kern_s / 1e12
     hbm_ach = frames * BYTES_PER_FRAME_FUSED / kern_s / 1e9
     roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": frames * NCU_DRAM_BYTES_PER_FRAME if a.ffn_impl == "tc" else None,
+                "traffic": frames * NCU_DRAM_BYTES_PER_FRAME if a.ffn_impl != "fp32" else None,
                 "traffic_note": "bytes per launch = frames x 327.5 B/frame from the ncu capture in profiles/ "
                                 "(algorithmic 321 B/frame: no re-reads)",
-                "kernel": "fused_kernel<2,%d> (MFCC+FFN VAD, FFN on %s)" % (
-                    1 if a.ffn_impl == "tc" else 0, "tcgen05 tf32x3" if a.ffn_impl == "tc" else "FP32 CUDA cores"), "launches_per_step": 1,
+                "kernel": "%s (MFCC+FFN VAD, FFN on %s)" % (
+                    {"tc16": "fused_kernel<2,2>", "tc": "fused_kernel<2,1>", "fp32": "fused_kernel<2,0>"}[a.ffn_impl],
+                    {"tc16": "tcgen05 kind::f16, statically scaled fp16 hi/lo operands",
+                     "tc": "tcgen05 kind::tf32, hi/lo operands", "fp32": "FP32 CUDA cores"}[a.ffn_impl]),
+                "launches_per_step": 1,
                 "algorithmic_flop_per_frame": FLOP_PER_FRAME_FUSED, "frames_per_launch": int(frames),
                 "peak_source": peak_src, "nominal_fp32_tflops": FP32_NOMINAL_TFLOPS,
                 "frac_of_nominal": achieved / FP32_NOMINAL_TFLOPS,

@@ -190,7 +190,9 @@ int vadb200_stream_feed(vadb200_bank* b, const int16_t* d_chunks /* [n][160], de
 int vadb200_synth_pcm(vadb200_handle* h, int16_t* d_out, int64_t n_utt, int64_t utt_samples,
                       int64_t utt_stride, uint32_t seed, int64_t first_utt, void* stream);
 /* FP32 FMA-pipe microbenchmark: the roofline denominator (MEASURED_PEAKS.json has none).
- * variant 0: register operands, 1: constant-bank operand.  Returns TFLOP/s (2 flop per FMA). */
+ * variant 0: FFMA register operands, 1: FFMA constant-bank operand, 2: packed FFMA2 register operands,
+ * 3: packed FFMA2 with an immediate multiplicand, 4 / 5 / 6: 8 FFMA2 chains interleaved with 8 / 4 / 0
+ * scalar FFMA chains (sub-pipe co-issue probe).  Returns TFLOP/s (2 flop per FMA). */
 int vadb200_fp32_peak(vadb200_handle* h, int variant, int iters, double* tflops_out);
 /* number of kernel launches issued by this library since load (for bench's gpu_launches) */
 int64_t vadb200_launch_count(void);

@@ -1,8 +1,10 @@
 """Loader that imports the UNMODIFIED reference (python-2 code) under python 3.
 
-TEST INFRASTRUCTURE.  Only usable where /root/reference exists (the build container);
-used by ``oracle/make_golden.py`` to freeze fixtures and by ``tests/test_oracle.py`` to
-re-pin the restatement against the live reference.  Recipe: SURVEY.md appendix C.
+TEST INFRASTRUCTURE.  Sources come from /root/reference where it is mounted (the build container)
+or from the byte-identical staged copy oracle/_ref/ (``oracle/make_ref.py``; git-ignored, travels
+to the GPU box).  Used by ``oracle/make_golden.py`` to freeze fixtures, by ``tests/test_oracle.py``
+to re-pin the restatement against the live reference, and by ``oracle/cpu_bench.py`` to time the
+reference's own code.  Recipe: SURVEY.md appendix C.
 """
 import os
 import pickle
@@ -11,6 +13,7 @@ import tempfile
 import types
 
 REFERENCE_ROOT = "/root/reference"
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 
 class Py2Int(int):
@@ -20,8 +23,16 @@ class Py2Int(int):
         return Py2Int(int.__floordiv__(self, o)) if isinstance(o, int) else float(self) / o
 
 
+def root():
+    """Directory the reference modules are imported from, or None."""
+    if os.path.isfile(os.path.join(REFERENCE_ROOT, "mfcc.py")):
+        return REFERENCE_ROOT
+    from . import make_ref
+    return STAGED_ROOT if make_ref.staged_ok() else None
+
+
 def available():
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "mfcc.py"))
+    return root() is not None
 
 
 _cache = {}
@@ -32,10 +43,10 @@ def load():
     ``sklearn_analyser`` and the python-2-int ``FFT_N``."""
     if "ns" in _cache:
         return _cache["ns"]
-    if not available():
-        raise RuntimeError("reference not mounted at %s" % REFERENCE_ROOT)
-    for p in (os.path.join(REFERENCE_ROOT, "dataset"),
-              os.path.join(REFERENCE_ROOT, "realtime_analysis"), REFERENCE_ROOT):
+    base = root()
+    if base is None:
+        raise RuntimeError("reference neither mounted at %s nor staged under oracle/_ref" % REFERENCE_ROOT)
+    for p in (os.path.join(base, "dataset"), os.path.join(base, "realtime_analysis"), base):
         if p not in sys.path:
             sys.path.insert(0, p)
     sys.modules.setdefault("cPickle", pickle)                 # sklearn_analyser.py:1
@@ -49,6 +60,6 @@ def load():
     finally:
         os.chdir(cwd)
     ns = types.SimpleNamespace(mfcc=ref_mfcc, file_processing=ref_fp, sklearn_analyser=ref_an,
-                               FFT_N=Py2Int(512))
+                               FFT_N=Py2Int(512), root=base)
     _cache["ns"] = ns
     return ns

@@ -43,7 +43,7 @@ def _uniform_batch(h, n_utt, L, seed):
     return pcm, off, ln, stride
 
 
-@pytest.mark.parametrize("impl", ["tc", "fp32"])
+@pytest.mark.parametrize("impl", ["tc16", "tc", "fp32"])
 def test_cfg3_bench_layout_one_segment_per_utterance(hw, impl):
     """The bench's decomposition: every 10 s utterance is ONE 997-frame segment (32 steps, 8 block
     phases, ring wraps).  1200 utterances = 1.19 M rows; 10 sampled utterances against the oracle:
@@ -85,7 +85,7 @@ def test_cfg3_bench_layout_one_segment_per_utterance(hw, impl):
     aplan = runtime.Plan(h, off, ln, runtime.MODE_VAD)
     assert aplan.segment_frames < 1024 and aplan.segment_count > n_utt
     assert torch.equal(aplan.vad(pcm)[0].view(n_utt, 993), labels)
-    h.set_ffn_impl("tc")
+    h.set_ffn_impl("tc16")
 
 
 def test_cfg2_mfcc_only_at_1024_utterances(hw):
@@ -156,7 +156,7 @@ def test_feat_dataset_inside_vad_kernel_and_windows(hw):
     utts = [synth_utterance(19, i, n) for i, n in enumerate((16000, 48017, 160000, 2001))]
     flat, off, ln = batch.pack_utterances(utts)
     pcm = flat.to(h.device)
-    for impl in ("tc", "fp32"):
+    for impl in ("tc16", "tc", "fp32"):
         h.set_ffn_impl(impl)
         plan = runtime.Plan(h, off, ln, runtime.MODE_VAD)
         labels, logits, feats = plan.vad(pcm, want_logits=True, want_feats=True, feat_mode=runtime.FEAT_DATASET)
@@ -166,7 +166,7 @@ def test_feat_dataset_inside_vad_kernel_and_windows(hw):
             check_vad(la, lo, u, w, mode="dataset")
             ref_rows = rm.dataset_features(rm.mfcc_utterance(u))
             assert rows_close(feats[ro[i]:ro[i + 1]].cpu().numpy(), ref_rows)
-    h.set_ffn_impl("tc")
+    h.set_ffn_impl("tc16")
     c = rm.mfcc_utterance(utts[1])
     win = np.lib.stride_tricks.sliding_window_view(c, 5, axis=0)[: c.shape[0] - 5].transpose(0, 2, 1)
     la, lo, fe = h.vad_windows(np.ascontiguousarray(win, dtype=np.float32), runtime.FEAT_DATASET, want_feats=True)
@@ -270,7 +270,7 @@ def test_two_threads_two_handles_different_classifiers(hw):
         except BaseException as ex:  # noqa: BLE001 -- reported by the main thread
             results[name] = repr(ex)
 
-    ts = [threading.Thread(target=worker, args=("a", 101, "tc")), threading.Thread(target=worker, args=("b", 202, "fp32")),
+    ts = [threading.Thread(target=worker, args=("a", 101, "tc16")), threading.Thread(target=worker, args=("b", 202, "fp32")),
           threading.Thread(target=worker, args=("c", 303, "tc"))]
     for t in ts:
         t.start()
@@ -313,7 +313,7 @@ def test_cfg4_4096_streams_against_offline_labels(hw):
     for j in range(12):
         lab = bank2.feed(allpcm[:, 160 * j:160 * (j + 1)])
         assert np.array_equal(lab, got[:, j])
-    h.set_ffn_impl("tc")
+    h.set_ffn_impl("tc16")
 
 
 def test_bit_identical_frames_define_nan_rows(hw):

@@ -20,9 +20,10 @@ from _parity import (MFCC_ATOL, MFCC_RTOL, LOGIT_ATOL, LOGIT_RTOL, ROW_ATOL, ROW
 CASES = ["synth_1p5s", "synth_ragged", "exact_fit", "too_short", "silence_dc", "tone_noise"]
 
 
-@pytest.fixture(scope="module", params=["tc", "fp32"])
+@pytest.fixture(scope="module", params=["tc16", "tc", "fp32"])
 def env(request):
-    """Every test runs under both FFN implementations: tcgen05 tf32x3 (default) and FP32 CUDA cores."""
+    """Every test runs under all three FFN implementations: tcgen05 fp16 hi/lo (default), tcgen05 tf32 hi/lo and
+    FP32 CUDA cores."""
     import torch
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
     from vad_b200 import runtime
@@ -30,9 +31,9 @@ def env(request):
     h = runtime.default_handle()
     h.set_ffn_weights(w)
     h.set_ffn_impl(request.param)
-    assert h.ffn_impl == {"fp32": 0, "tc": 1}[request.param]
+    assert h.ffn_impl == {"fp32": 0, "tc": 1, "tc16": 2}[request.param]
     yield h, w
-    h.set_ffn_impl("tc")
+    h.set_ffn_impl("tc16")
 
 
 @pytest.fixture(scope="module")
@@ -202,18 +203,18 @@ def test_host_pipeline_equals_device_path(env):
 
 
 # ---- tensor-core FFN (tcgen05, tf32 x3) ----------------------------------------------------------
-@pytest.fixture()
-def tc(env):
+@pytest.fixture(params=["tc16", "tc"])
+def tc(env, request):
     h, w = env
     prev = h.ffn_impl
-    h.set_ffn_impl("tc")
+    h.set_ffn_impl(request.param)
     yield h, w
     h.set_ffn_impl(prev)
 
 
 def test_tc_ffn_rows_vs_oracle(tc):
     h, w = tc
-    assert h.ffn_impl == 1
+    assert h.ffn_impl in (1, 2)
     rng = np.random.default_rng(5)
     for n in (1, 127, 128, 129, 1000):
         x = (rng.standard_normal((n, 39)) * np.array([1.0] * 13 + [3.0] * 13 + [30.0] * 13)).astype(np.float32)
@@ -266,18 +267,19 @@ def test_tc_and_fp32_paths_agree_on_batch(env):
     prev = h.ffn_impl
     h.set_ffn_impl("fp32")
     la0, lo0, _ = plan.vad(pcm, want_logits=True)
-    h.set_ffn_impl("tc")
     try:
-        la1, lo1, _ = plan.vad(pcm, want_logits=True)
-        la2, _, _ = plan.vad(pcm)
+        for impl in ("tc", "tc16"):
+            h.set_ffn_impl(impl)
+            la1, lo1, _ = plan.vad(pcm, want_logits=True)
+            la2, _, _ = plan.vad(pcm)
+            assert torch.equal(la1, la2)
+            d = (lo0 - lo1).abs()
+            fin = torch.isfinite(lo0).all(dim=1)
+            assert torch.equal(torch.isfinite(lo1).all(dim=1), fin)
+            assert float(d[fin].max()) < 5e-4
+            assert float((la0 != la1).float().mean()) < 1e-3
     finally:
         h.set_ffn_impl(prev)
-    assert torch.equal(la1, la2)
-    d = (lo0 - lo1).abs()
-    fin = torch.isfinite(lo0).all(dim=1)
-    assert torch.equal(torch.isfinite(lo1).all(dim=1), fin)
-    assert float(d[fin].max()) < 5e-4
-    assert float((la0 != la1).float().mean()) < 1e-3
 
 
 # ---- analyser / streaming ------------------------------------------------------------------------

@@ -25,9 +25,14 @@
 // LBO = 2N/8 * 128 B) are prepared once on the host and arrive in shared memory by one TMA bulk copy.
 #pragma once
 
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
+#include <cstring>
+#include <vector>
 
 #include "vad_core.cuh"
 
@@ -82,6 +87,101 @@ inline void tc_pack_weights(const FfnParams& p, unsigned char* blob /*kTcBlobByt
   tc_pack_layer(p.W2, kH1, kH2, kTcK2, kTcN2, reinterpret_cast<float*>(blob + kTcOff2));
   tc_pack_layer(p.W3, kH2, kH3, kTcK3, kTcN3, reinterpret_cast<float*>(blob + kTcOff3));
   tc_pack_layer(p.W4, kH3, kNCls, kTcK4, kTcN4, reinterpret_cast<float*>(blob + kTcOff4));
+}
+
+// ---- fp16 hi/lo operand path (kind::f16, K = 16 per instruction: half the MMAs of the tf32 path) -------
+// Same three-product scheme with x = x_hi + x_lo in fp16 (11-bit significands, like tf32).  fp16's narrow
+// exponent range is handled statically: every layer's weights are scaled by a power of two sw_l into
+// [8192, 16384), every layer's input activations by a power of two sa_l chosen from a rigorous bound on
+// their magnitude (features are bounded by the MFCC range, hidden activations by sum |W| x bound), so no
+// operand can overflow; the epilogue multiplies D by 1 / (sw_l sa_l) (exact).  A handle whose weights
+// would need an absurd scale keeps the tf32 path.
+constexpr int kTc16Blk1 = kTcK1 * kTcN1 * 2, kTc16Blk2 = kTcK2 * kTcN2 * 2, kTc16Blk3 = kTcK3 * kTcN3 * 2,
+              kTc16Blk4 = kTcK4 * kTcN4 * 2;          // bytes of one [K][N] fp16 block; hi | lo doubles it
+constexpr int kTc16Off1 = 0;
+constexpr int kTc16Off2 = kTc16Off1 + 2 * kTc16Blk1;
+constexpr int kTc16Off3 = kTc16Off2 + 2 * kTc16Blk2;
+constexpr int kTc16Off4 = kTc16Off3 + 2 * kTc16Blk3;
+constexpr int kTc16BlobBytes = kTc16Off4 + 2 * kTc16Blk4;  // 23,552
+// rigorous feature bounds (vad_core.cuh window_features): |z| <= 2 (n = 5), |c| <= 1353 (|log2 E| <= 52 times the
+// largest row sum of the folded DCT matrix), so |d1| <= 2706 and |d2| <= 5412 in either feature recipe
+constexpr float kFeatBoundZ = 1353.0f, kFeatBoundD1 = 2706.0f, kFeatBoundD2 = 5416.0f;
+
+inline uint16_t f32_to_f16_rn(float f) {  // round-to-nearest-even, subnormals, no NaN inputs expected
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  x &= 0x7FFFFFFFu;
+  if (x >= 0x47800000u) return static_cast<uint16_t>(sign | 0x7C00u);  // overflow -> inf (never: scales prevent it)
+  if (x < 0x38800000u) {                                               // subnormal half (or zero)
+    if (x < 0x33000000u) return static_cast<uint16_t>(sign);
+    const uint32_t mant = (x & 0x7FFFFFu) | 0x800000u;
+    const int shift = 126 - static_cast<int>(x >> 23);                // 14 .. 24
+    uint32_t h = mant >> shift;
+    const uint32_t rem = mant & ((1u << shift) - 1u), half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (h & 1u))) ++h;
+    return static_cast<uint16_t>(sign | h);
+  }
+  uint32_t h = ((x >> 23) - 112u) << 10 | ((x >> 13) & 0x3FFu);
+  const uint32_t rem = x & 0x1FFFu;
+  if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) ++h;
+  return static_cast<uint16_t>(sign | h);
+}
+inline float f16_to_f32(uint16_t h) {
+  const uint32_t sign = (h & 0x8000u) << 16, e = (h >> 10) & 0x1Fu, m = h & 0x3FFu;
+  if (e == 0) return (sign ? -1.0f : 1.0f) * std::ldexp(static_cast<float>(m), -24);
+  uint32_t x = sign | ((e + 112u) << 23) | (m << 13);
+  float f;
+  memcpy(&f, &x, 4);
+  return f;
+}
+inline void tc16_pack_layer(const float* W /*[k_real][n_real]*/, int k_real, int n_real, int K, int N, float sw,
+                            uint16_t* blk, bool permute_features = false) {
+  for (int i = 0; i < 2 * K * N; ++i) blk[i] = 0;
+  for (int n = 0; n < n_real; ++n)
+    for (int kk = 0; kk < k_real; ++kk) {
+      const float w = W[kk * n_real + n] * sw;
+      const int k = permute_features ? tc_feat_col(kk) : kk;
+      const uint16_t hi = f32_to_f16_rn(w);
+      const uint16_t lo = f32_to_f16_rn(w - f16_to_f32(hi));
+      const int ihi = ((k / 8) * (2 * N / 8) + (n / 8)) * 64 + (n % 8) * 8 + (k % 8);
+      const int ilo = ((k / 8) * (2 * N / 8) + ((N + n) / 8)) * 64 + ((N + n) % 8) * 8 + (k % 8);
+      blk[ihi] = hi;
+      blk[ilo] = lo;
+    }
+}
+// Chooses the scales, packs the blob, fills bias.post / bias.pre.  Returns false if a scale exponent is
+// out of the range the scheme was validated for (the handle then keeps the tf32 path).
+inline bool tc16_pack_weights(const FfnParams& p, unsigned char* blob /*kTc16BlobBytes*/, FfnBias& fb) {
+  const float* W[4] = {p.W1, p.W2, p.W3, p.W4};
+  const float* B[4] = {p.b1, p.b2, p.b3, p.b4};
+  const int kin[4] = {kNFeat, kH1, kH2, kH3}, nout[4] = {kH1, kH2, kH3, kNCls};
+  const int Kp[4] = {kTcK1, kTcK2, kTcK3, kTcK4}, Np[4] = {kTcN1, kTcN2, kTcN3, kTcN4};
+  const int off[4] = {kTc16Off1, kTc16Off2, kTc16Off3, kTc16Off4};
+  std::vector<double> bound(kNFeat);
+  for (int i = 0; i < kNFeat; ++i) bound[i] = i < kNCep ? kFeatBoundZ : i < 2 * kNCep ? kFeatBoundD1 : kFeatBoundD2;
+  for (int l = 0; l < 4; ++l) {
+    double amax = 0.0, wmax = 0.0;
+    for (double b : bound) amax = std::max(amax, b);
+    for (int i = 0; i < kin[l] * nout[l]; ++i) wmax = std::max(wmax, static_cast<double>(std::fabs(W[l][i])));
+    if (!(amax < 1e30) || !(wmax < 1e30)) return false;
+    // activations into (-32768, 32768), weights into [8192, 16384)
+    const int ea = amax > 32000.0 ? static_cast<int>(std::ceil(std::log2(amax / 32000.0))) : 0;
+    const int ew = wmax > 0.0 ? static_cast<int>(std::floor(std::log2(16000.0 / wmax))) : 0;
+    if (ea > 60 || ew > 60 || ew < -60) return false;
+    const float sa = std::ldexp(1.0f, -ea), sw = std::ldexp(1.0f, ew);
+    fb.pre[l] = sa;
+    fb.post[l] = std::ldexp(1.0f, ea - ew);
+    tc16_pack_layer(W[l], kin[l], nout[l], Kp[l], Np[l], sw, reinterpret_cast<uint16_t*>(blob + off[l]), l == 0);
+    std::vector<double> nb(nout[l]);
+    for (int j = 0; j < nout[l]; ++j) {
+      double s = std::fabs(static_cast<double>(B[l][j]));
+      for (int i = 0; i < kin[l]; ++i) s += std::fabs(static_cast<double>(W[l][i * nout[l] + j])) * bound[i];
+      nb[j] = s;
+    }
+    bound = nb;
+  }
+  return true;
 }
 
 #if defined(__CUDACC__)
@@ -326,6 +426,146 @@ __device__ __forceinline__ uint32_t ffn_tc_tile(const FfnBias& fb, float (&logit
   tc_fence_before();  // the next tile's tcgen05.st must not overtake these loads
   VADB_TS(15);
 #undef VADB_TS
+  return par;
+}
+
+// ======================================= fp16 hi/lo variant ===========================================
+// A operand in TMEM: two fp16 per 32-bit column (element 2c in the low half), hi parts in columns
+// [0, K/2), lo parts in [K/2, K).  One instruction covers K = 16 = 8 columns.
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__host__ __device__ constexpr uint32_t tc16_idesc(int n) {
+  return (1u << 4) /* D = f32; A = B = f16 (format 0), both K-major */ | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(128 >> 4) << 24);
+}
+template <int K, int N>
+__device__ __forceinline__ void tc16_issue_layer(uint32_t tm_base, uint32_t d_col, uint32_t w_smem, uint64_t* done_bar) {
+  constexpr uint32_t lbo = (2 * N / 8) * 128, sbo = 128;   // core matrix = 8 rows x 8 fp16
+  constexpr uint32_t idesc_2n = tc16_idesc(2 * N), idesc_n = tc16_idesc(N);
+  const uint32_t a_hi = tm_base + kTmA, a_lo = tm_base + kTmA + K / 2, d = tm_base + d_col;
+#pragma unroll
+  for (int j = 0; j < K / 16; ++j) {
+    const uint64_t b = tc_smem_desc(w_smem + 2 * j * lbo, lbo, sbo);
+    umma_f16_ts(d, a_hi + 8 * j, b, idesc_2n, j > 0 ? 1u : 0u);
+    umma_f16_ts(d, a_lo + 8 * j, b, idesc_n, 1u);
+  }
+  umma_commit(done_bar);
+}
+// (x0, x1) -> one 32-bit word of hi parts and one of lo parts (element 0 in the low half)
+__device__ __forceinline__ void tc16_split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// Epilogue of a hidden layer: D (NOUT fp32 columns at d_col, second half NOUT further) -> x post-scale, + bias,
+// ReLU, x pre-scale of the next layer, fp16 hi/lo split -> A operand of the next layer.
+template <int NOUT, int HALVES>
+__device__ __forceinline__ void tc16_hidden_epilogue(uint32_t tl, uint32_t d_col, const float* bias, float post,
+                                                     float pre_next, int hidx) {
+  constexpr int W = NOUT / HALVES;         // fp32 columns per thread: 64, 32, 16 or 8
+  constexpr int CH = W >= 16 ? 16 : 8;
+  const int base = hidx * W;
+#pragma unroll
+  for (int c0 = 0; c0 < W; c0 += CH) {
+    uint32_t v[CH], u[CH], hi[CH / 2], lo[CH / 2];
+    if constexpr (CH == 16) {
+      tmem_ld16(tl + d_col + base + c0, v);
+      tmem_ld16(tl + d_col + NOUT + base + c0, u);
+    } else {
+      tmem_ld8(tl + d_col + base + c0, v);
+      tmem_ld8(tl + d_col + NOUT + base + c0, u);
+    }
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < CH; i += 2) {
+      const float a0 = fmaxf(fmaf(__uint_as_float(v[i]) + __uint_as_float(u[i]), post, bias[base + c0 + i]), 0.0f);
+      const float a1 =
+          fmaxf(fmaf(__uint_as_float(v[i + 1]) + __uint_as_float(u[i + 1]), post, bias[base + c0 + i + 1]), 0.0f);
+      tc16_split2(a0 * pre_next, a1 * pre_next, hi[i / 2], lo[i / 2]);
+    }
+    if constexpr (CH == 16) {
+      tmem_st8(tl + kTmA + (base + c0) / 2, hi);
+      tmem_st8(tl + kTmA + NOUT / 2 + (base + c0) / 2, lo);
+    } else {
+      tmem_st4(tl + kTmA + (base + c0) / 2, hi);
+      tmem_st4(tl + kTmA + NOUT / 2 + (base + c0) / 2, lo);
+    }
+  }
+  tmem_wait_st();
+}
+// 24 layer-1 A columns of one half (features of coefficients 0-6 / 7-12) -> 12 + 12 packed columns.
+__device__ __forceinline__ void tc16_store_a1_half(uint32_t tl, int hidx, const float (&xl)[24], float pre) {
+  uint32_t hi[8], lo[8], hi4[4], lo4[4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tc16_split2(xl[2 * i] * pre, xl[2 * i + 1] * pre, hi[i], lo[i]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) tc16_split2(xl[16 + 2 * i] * pre, xl[17 + 2 * i] * pre, hi4[i], lo4[i]);
+  const uint32_t b = tl + kTmA + 12 * hidx;
+  tmem_st8(b, hi);
+  tmem_st4(b + 8, hi4);
+  tmem_st8(b + kTcK1 / 2, lo);
+  tmem_st4(b + kTcK1 / 2 + 8, lo4);
+}
+// The whole FFN for one 128-frame tile on fp16 operands; same contract as ffn_tc_tile.
+template <int HALVES>
+__device__ __forceinline__ uint32_t ffn_tc16_tile(const FfnBias& fb, float (&logit)[kNCls], uint32_t tm_base, int wq,
+                                                  int hidx, bool is_issuer, uint32_t w_smem, uint64_t* mma_bar,
+                                                  uint32_t par) {
+  const uint32_t tl = tm_base + (static_cast<uint32_t>(32 * wq) << 16);
+  tmem_wait_st();
+  tc_fence_before();
+  tc_bar<HALVES>();
+  if (is_issuer) {
+    tc_fence_after();
+    tc16_issue_layer<kTcK1, kTcN1>(tm_base, kTmD1, w_smem + kTc16Off1, mma_bar);
+  }
+  tc_mbar_wait(mma_bar, par); par ^= 1u;
+  tc_fence_after();
+  tc16_hidden_epilogue<kTcN1, HALVES>(tl, kTmD1, fb.b1, fb.post[0], fb.pre[1], hidx);
+  tc_fence_before();
+  tc_bar<HALVES>();
+  if (is_issuer) {
+    tc_fence_after();
+    tc16_issue_layer<kTcK2, kTcN2>(tm_base, kTmD2, w_smem + kTc16Off2, mma_bar);
+  }
+  tc_mbar_wait(mma_bar, par); par ^= 1u;
+  tc_fence_after();
+  tc16_hidden_epilogue<kTcN2, HALVES>(tl, kTmD2, fb.b2, fb.post[1], fb.pre[2], hidx);
+  tc_fence_before();
+  tc_bar<HALVES>();
+  if (is_issuer) {
+    tc_fence_after();
+    tc16_issue_layer<kTcK3, kTcN3>(tm_base, kTmD3, w_smem + kTc16Off3, mma_bar);
+  }
+  tc_mbar_wait(mma_bar, par); par ^= 1u;
+  tc_fence_after();
+  tc16_hidden_epilogue<kTcN3, HALVES>(tl, kTmD3, fb.b3, fb.post[2], fb.pre[3], hidx);
+  tc_fence_before();
+  tc_bar<HALVES>();
+  if (is_issuer) {
+    tc_fence_after();
+    tc16_issue_layer<kTcK4, kTcN4>(tm_base, kTmD4, w_smem + kTc16Off4, mma_bar);
+  }
+  tc_mbar_wait(mma_bar, par); par ^= 1u;
+  tc_fence_after();
+  if (hidx == 0) {
+    uint32_t v[8], u[8];
+    tmem_ld8(tl + kTmD4, v);
+    tmem_ld8(tl + kTmD4 + kTcN4, u);
+    tmem_wait_ld();
+#pragma unroll
+    for (int o = 0; o < kNCls; ++o) logit[o] = fmaf(__uint_as_float(v[o]) + __uint_as_float(u[o]), fb.post[3], fb.b4[o]);
+  }
+  tc_fence_before();  // the next tile's tcgen05.st must not overtake these loads
   return par;
 }
 #endif  // __CUDACC__

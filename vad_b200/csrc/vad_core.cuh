@@ -75,6 +75,8 @@ struct FfnParams {
 };
 struct FfnBias {                 // what the tensor-core FFN needs besides its weight blob
   float b1[kH1], b2[kH2], b3[kH3], b4[kNCls], pad_[1];
+  float pre[4];                  // fp16 operand path: power-of-two scale of layer l's input activations
+  float post[4];                 // ... and the exact inverse of (weight scale x activation scale)
 };
 struct FfnNone { int unused; };
 

@@ -51,6 +51,7 @@ constexpr int kOffSeg = kOffBar + 32;                                       // 4
 constexpr int kFusedSmemBytes = kOffSeg + 16;                               // s_seg, s_tmem
 constexpr int kBlockStepsTc = 4;                                            // tensor-core FFN: one M=128 tile
 static_assert(kTcBlobBytes <= kWarps * 2 * kExchFrame * 8 + kBins * kPPitch * 4, "weight blob must fit exch + P");
+static_assert(2 * (kFusedSmemBytes + 1024) <= 233472, "two CTAs per SM");
 
 struct Segment {
   long long pcm_start;  // sample index of the first frame's first sample (multiple of 8)
@@ -142,7 +143,9 @@ __host__ __device__ __forceinline__ int slot_of_col(int c) { return (c & ~3) | (
 // Four frames of a warp through the FFT: half-warp h = lanes 16h..16h+15, two frames per thread.
 // w32a: first PCM word of frame A; frame B starts `delta` words later.  ex: this half-warp's
 // transpose scratch (kExchFrame 64-bit slots).  Powers go to P columns col, col + 1.
-template <int NZ>
+// Bins below FIRST are not stored (the mel filterbank starts at bin 10): s_P may then point FIRST rows
+// before a tile that holds rows FIRST .. 255 only.
+template <int NZ, int FIRST = 0>
 __device__ __forceinline__ void warp_fft_quad(const uint32_t* w32a, int delta, f2* ex, const cf2* s_tw1,
                                                const cf2* s_tw2, float* s_P, int col, int lane) {
   const int t = lane & 15;
@@ -159,7 +162,7 @@ __device__ __forceinline__ void warp_fft_quad(const uint32_t* w32a, int delta, f
   __syncwarp();
   dft16<16>(xr, xi);
   fft_split_store(xr, xi, t, s_tw2, ShflXchg{lane}, [&](int bin, f2 v) {
-    *reinterpret_cast<f2*>(s_P + bin * kPPitch + col) = v;
+    if (FIRST == 0 || bin >= FIRST) *reinterpret_cast<f2*>(s_P + bin * kPPitch + col) = v;
   });
 }
 
@@ -181,12 +184,12 @@ __device__ __forceinline__ void warp_fft_pair(LOAD&& load, cf2* ex, const cf2* s
 
 // Coalesced store of `total` consecutive floats starting at dst: a scalar head up to the first 16-byte
 // boundary, 128-bit stores, scalar tail.  gen(j, v, cnt) produces elements j .. j + cnt - 1 (cnt <= 4).
-template <class GEN>
+template <int NTHREADS = kThreads, class GEN>
 __device__ __forceinline__ void flush_flat(float* dst, int total, int tid, GEN&& gen) {
   if (total <= 0) return;
   const int head = min(total, static_cast<int>((16u - (reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u) >> 2);
   const int nq = (total - head) >> 2;
-  for (int q = tid; q < nq; q += kThreads) {
+  for (int q = tid; q < nq; q += NTHREADS) {
     float v[4];
     gen(head + 4 * q, v, 4);
     *reinterpret_cast<float4*>(dst + head + 4 * q) = make_float4(v[0], v[1], v[2], v[3]);
@@ -197,7 +200,9 @@ __device__ __forceinline__ void flush_flat(float* dst, int total, int tid, GEN&&
     if (cnt > 0) {
       float v[4];
       gen(j0, v, cnt);
-      for (int i = 0; i < cnt; ++i) dst[j0 + i] = v[i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i < cnt) dst[j0 + i] = v[i];
     }
   }
 }
@@ -227,12 +232,14 @@ __device__ __forceinline__ void classify_row(const FfnParams& w, const float (&r
 }
 
 // MODE 0: MFCC rows [T][13]; 1: dataset rows [T-5][39]; 2: VAD labels [T-5].
-// TC (MODE 2 only): 0 = FFN on FP32 CUDA cores, 1 = FFN on tcgen05 (tf32 x3, TMEM accumulators).
+// TC (MODE 2 only): 0 = FFN on FP32 CUDA cores, 1 = FFN on tcgen05 kind::tf32 (hi/lo split, TMEM accumulators),
+// 2 = tcgen05 kind::f16 on statically scaled fp16 hi/lo operands (half the MMAs, half the weight blob).
 // FFN argument of the kernel variant: nothing (MFCC / dataset rows), the full FP32 weights, or the biases
 // only (tensor-core FFN: the weights are the per-handle tcgen05 operand blob in global memory).
 template <int MODE, int TC> struct FfnArgOf { using type = FfnNone; };
 template <> struct FfnArgOf<2, 0> { using type = FfnParams; };
 template <> struct FfnArgOf<2, 1> { using type = FfnBias; };
+template <> struct FfnArgOf<2, 2> { using type = FfnBias; };
 
 template <int MODE, int TC>
 __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constant__ FusedParams p,
@@ -321,6 +328,8 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
       __syncthreads();
 
       // ---- mel + log phase -----------------------------------------------------------------
+      // (a rolled, table-driven mel loop -- one small code body for all warps, weights in shared memory -- was
+      // measured 5.8 % slower than these eight straight-line regions: its loads are latency-exposed)
       if (!(VADB_DBG(p) & 2)) mel_group_dispatch<kPPitch, 32>(warp, s_P + lane, s_logE + lane);
       const int computed = min((s + 1) * kStepFrames, n);
       const bool block_now = (((s + 1) % kBlk) == 0 || s == nsteps - 1) && !(VADB_DBG(p) & 8);
@@ -328,8 +337,9 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
       if (tc_now) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // exch/P generic accesses before the TMA overwrite
       __syncthreads();
       if (tc_now && tid == 0 && !(VADB_DBG(p) & 16)) {  // exch + P are idle until the next FFT phase: land the weight blob during the DCT
-        mbar_arrive_expect_tx(&s_bar[2], kTcBlobBytes);
-        bulk_g2s(smem + kOffExch, p.tc_blob, kTcBlobBytes, &s_bar[2]);
+        constexpr uint32_t blob_bytes = TC == 2 ? kTc16BlobBytes : kTcBlobBytes;
+        mbar_arrive_expect_tx(&s_bar[2], blob_bytes);
+        bulk_g2s(smem + kOffExch, p.tc_blob, blob_bytes, &s_bar[2]);
       }
 
       // ---- DCT phase -> MFCC ring -----------------------------------------------------------
@@ -425,7 +435,8 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
               }
               s_logE[tid] = ok_half ? 1.0f : 0.0f;
               if (ts) ts[1] = clock64();
-              tc_store_a1_half(tl, hidx, xl);
+              if constexpr (TC == 2) tc16_store_a1_half(tl, hidx, xl, ffn.pre[0]);
+              else tc_store_a1_half(tl, hidx, xl);
               if (p.feats && valid) {
                 const long long row = seg.out_start - p.row_base + (c - 2);
                 const int k0 = hidx ? 7 : 0, nk = hidx ? 6 : 7;
@@ -438,6 +449,8 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
               if constexpr (TC == 1)
                 mma_par = ffn_tc_tile<2>(ffn, logit, tm_base, warp & 3, hidx, tid == 0, smem_u32(wdst), &s_bar[3], mma_par,
                                          ts, VADB_DBG(p));
+              if constexpr (TC == 2)
+                mma_par = ffn_tc16_tile<2>(ffn, logit, tm_base, warp & 3, hidx, tid == 0, smem_u32(wdst), &s_bar[3], mma_par);
               ++dbg_n;
               if (valid && hidx == 0) {
                 const bool ok = s_logE[fr] != 0.0f && s_logE[128 + fr] != 0.0f;  // ordered by the tile's bar.syncs
@@ -483,9 +496,11 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
 // Stand-alone tensor-core FFN over feature rows [n][39] (classifier.predict duck type): one CTA =
 // one 128-row tile.  Same tile routine as the fused kernel's block phase.
 constexpr int kFfnTcSmemBytes = kTcBlobBytes + 64;
+template <int KIND>  // 1: tf32 operands, 2: fp16 operands
 __global__ void __launch_bounds__(128) ffn_tc_rows_kernel(const float* x, long long n, const unsigned char* blob,
                                                           uint8_t* labels, float* logits,
                                                           const __grid_constant__ FfnBias fb) {
+  constexpr uint32_t kBlob = KIND == 2 ? kTc16BlobBytes : kTcBlobBytes;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcBlobBytes);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + kTcBlobBytes + 32);
@@ -501,8 +516,8 @@ __global__ void __launch_bounds__(128) ffn_tc_rows_kernel(const float* x, long l
   tc_fence_after();
   const uint32_t tm_base = *s_tmem;
   if (tid == 0) {
-    mbar_arrive_expect_tx(&bars[0], kTcBlobBytes);
-    bulk_g2s(smem, blob, kTcBlobBytes, &bars[0]);
+    mbar_arrive_expect_tx(&bars[0], kBlob);
+    bulk_g2s(smem, blob, kBlob, &bars[0]);
   }
   const long long i = static_cast<long long>(blockIdx.x) * 128 + tid;
   const long long src = i < n ? i : n - 1;
@@ -525,10 +540,16 @@ __global__ void __launch_bounds__(128) ffn_tc_rows_kernel(const float* x, long l
       if (col < 24) h0[col] = v[f];
       else h1[col - 24] = v[f];
     }
-    tc_store_a1_half(tl, 0, h0);
-    tc_store_a1_half(tl, 1, h1);
+    if constexpr (KIND == 2) {
+      tc16_store_a1_half(tl, 0, h0, fb.pre[0]);
+      tc16_store_a1_half(tl, 1, h1, fb.pre[0]);
+    } else {
+      tc_store_a1_half(tl, 0, h0);
+      tc_store_a1_half(tl, 1, h1);
+    }
   }
-  ffn_tc_tile<1>(fb, logit, tm_base, warp, 0, tid == 0, smem_u32(smem), &bars[1], 0);
+  if constexpr (KIND == 2) ffn_tc16_tile<1>(fb, logit, tm_base, warp, 0, tid == 0, smem_u32(smem), &bars[1], 0);
+  else ffn_tc_tile<1>(fb, logit, tm_base, warp, 0, tid == 0, smem_u32(smem), &bars[1], 0);
   if (i < n) {
     uint8_t lab = decide(logit);
     if (!ok) {
@@ -938,37 +959,35 @@ __device__ __forceinline__ double warp_sum(double v) {
 __global__ void __launch_bounds__(256) scale_rows_kernel(float* rows, long long n_rows, int pass, double* acc) {
   const long long total = n_rows * kNFeat;
   const double cnt = static_cast<double>(n_rows) * kNCep;
-  double mean[3] = {0.0, 0.0, 0.0}, inv[3] = {0.0, 0.0, 0.0};
+  double m0 = 0.0, m1 = 0.0, m2 = 0.0, i0 = 0.0, i1 = 0.0, i2 = 0.0;
   if (pass >= 1) {
-#pragma unroll
-    for (int g = 0; g < 3; ++g) mean[g] = acc[g] / cnt;
+    m0 = acc[0] / cnt; m1 = acc[1] / cnt; m2 = acc[2] / cnt;
   }
-  if (pass == 2) {
-#pragma unroll
-    for (int g = 0; g < 3; ++g) inv[g] = 1.0 / sqrt(acc[3 + g] / cnt);  // std == 0 -> inf -> nan rows, as numpy
+  if (pass == 2) {  // std == 0 -> inf -> nan rows, as numpy
+    i0 = 1.0 / sqrt(acc[3] / cnt); i1 = 1.0 / sqrt(acc[4] / cnt); i2 = 1.0 / sqrt(acc[5] / cnt);
   }
-  double part[3] = {0.0, 0.0, 0.0};
+  double p0 = 0.0, p1 = 0.0, p2 = 0.0;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
   for (long long j = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; j < total; j += stride) {
     const int col = static_cast<int>(j % kNFeat);
     const int g = col / kNCep;
     const double v = static_cast<double>(rows[j]);
+    const double mean = g == 0 ? m0 : g == 1 ? m1 : m2;
     if (pass == 0) {
-      part[g] += v;
+      p0 += g == 0 ? v : 0.0; p1 += g == 1 ? v : 0.0; p2 += g == 2 ? v : 0.0;
     } else if (pass == 1) {
-      const double d = v - mean[g];
-      part[g] += d * d;
+      const double d = v - mean, dd = d * d;
+      p0 += g == 0 ? dd : 0.0; p1 += g == 1 ? dd : 0.0; p2 += g == 2 ? dd : 0.0;
     } else {
-      rows[j] = static_cast<float>((v - mean[g]) * inv[g]);
+      rows[j] = static_cast<float>((v - mean) * (g == 0 ? i0 : g == 1 ? i1 : i2));
     }
   }
   if (pass == 2) return;
   __shared__ double s_part[3][8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-  for (int g = 0; g < 3; ++g) {
-    const double w = warp_sum(part[g]);
-    if (lane == 0) s_part[g][warp] = w;
+  {
+    const double w0 = warp_sum(p0), w1 = warp_sum(p1), w2 = warp_sum(p2);
+    if (lane == 0) { s_part[0][warp] = w0; s_part[1][warp] = w1; s_part[2][warp] = w2; }
   }
   __syncthreads();
   if (threadIdx.x < 3) {
@@ -1039,6 +1058,57 @@ __global__ void __launch_bounds__(256) fp32_peak_kernel(float* sink, int iters, 
   float s = 0.0f;
 #pragma unroll
   for (int i = 0; i < 16; ++i) s += acc[i];
+  if (s == 123.456f) sink[0] = s;
+}
+// variant 2: packed FFMA2 (two fp32 FMAs per lane per instruction), 16 independent chains, register
+// multiplicand; variant 3: FFMA2 with an immediate (broadcast) multiplicand -- the butterfly form.
+template <int VARIANT>
+__global__ void __launch_bounds__(256) fp32x2_peak_kernel(float* sink, int iters, float m, float a) {
+  float2 acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = make_float2(static_cast<float>(threadIdx.x + i), static_cast<float>(i));
+  const float2 m2 = make_float2(m, m + 1e-7f), a2 = make_float2(a, a);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int rep = 0; rep < 8; ++rep) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        if (VARIANT == 2) acc[i] = __ffma2_rn(acc[i], m2, a2);
+        else acc[i] = __ffma2_rn(acc[i], make_float2(1.0000001f, 1.0000001f), a2);
+      }
+    }
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i].x + acc[i].y;
+  if (s == 123.456f) sink[0] = s;
+}
+// variant 4: 8 packed FFMA2 chains interleaved with NS scalar FFMA chains (does scalar work ride along on the
+// second FMA sub-pipe while packed work holds the first?).  flop per iteration-rep: 8 * 4 + NS * 2.
+template <int NS>
+__global__ void __launch_bounds__(256) fp32mix_peak_kernel(float* sink, int iters, float m, float a) {
+  float2 acc2[8];
+  float acc[NS > 0 ? NS : 1];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc2[i] = make_float2(static_cast<float>(threadIdx.x + i), static_cast<float>(i));
+#pragma unroll
+  for (int i = 0; i < NS; ++i) acc[i] = static_cast<float>(threadIdx.x - i);
+  const float2 a2 = make_float2(a, a);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int rep = 0; rep < 8; ++rep) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc2[i] = __ffma2_rn(acc2[i], make_float2(1.0000001f, 1.0000001f), a2);
+        if (i < NS) acc[i] = fmaf(acc[i], m, a);
+      }
+    }
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += acc2[i].x + acc2[i].y;
+#pragma unroll
+  for (int i = 0; i < NS; ++i) s += acc[i];
   if (s == 123.456f) sink[0] = s;
 }
 

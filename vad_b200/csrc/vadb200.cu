@@ -75,8 +75,10 @@ struct vadb200_handle {
   float* d_rows[kHostBufs] = {};
   long long stage_cap = 0, lab_cap = 0, lgt_cap = 0, rows_cap = 0;
   float* d_sink = nullptr;
-  unsigned char* d_tc_blob = nullptr;  // canonical tf32 hi/lo weight blob (ffn_tc.cuh)
-  int ffn_impl = 1;                    // 0: FP32 CUDA cores, 1: tcgen05 tf32 x3 (default)
+  unsigned char* d_tc_blob = nullptr;   // canonical tf32 hi/lo weight blob (ffn_tc.cuh)
+  unsigned char* d_tc16_blob = nullptr; // canonical fp16 hi/lo weight blob, statically scaled
+  bool tc16_ok = false;                 // the fp16 scales are in range for this handle's weights
+  int ffn_impl = 2;                     // 0: FP32 CUDA cores, 1: tcgen05 tf32 hi/lo, 2: tcgen05 fp16 hi/lo (default)
 };
 
 struct vadb200_plan {
@@ -121,7 +123,9 @@ int ensure_attrs(vadb200_handle* h) {
   CU(cudaFuncSetAttribute(fused_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes));
   CU(cudaFuncSetAttribute(fused_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes));
   CU(cudaFuncSetAttribute(fused_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes));
-  CU(cudaFuncSetAttribute(ffn_tc_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnTcSmemBytes));
+  CU(cudaFuncSetAttribute(fused_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFusedSmemBytes));
+  CU(cudaFuncSetAttribute(ffn_tc_rows_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnTcSmemBytes));
+  CU(cudaFuncSetAttribute(ffn_tc_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnTcSmemBytes));
   CU(cudaFuncSetAttribute(frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFramesSmemBytes));
   CU(cudaFuncSetAttribute(stream_feed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes));
   h->attr_set = true;
@@ -148,8 +152,14 @@ int launch_fused(vadb200_plan* p, FusedParams fp, int n_segs, cudaStream_t st) {
     case VADB200_MODE_MFCC: fused_kernel<0, 0><<<grid, kThreads, kFusedSmemBytes, st>>>(fp, FfnNone{0}); break;
     case VADB200_MODE_DATASET: fused_kernel<1, 0><<<grid, kThreads, kFusedSmemBytes, st>>>(fp, FfnNone{0}); break;
     default:
-      if (h->ffn_impl == 1) fused_kernel<2, 1><<<grid, kThreads, kFusedSmemBytes, st>>>(fp, h->bias);
-      else fused_kernel<2, 0><<<grid, kThreads, kFusedSmemBytes, st>>>(fp, h->par);
+      if (h->ffn_impl == 2 && h->tc16_ok) {
+        fp.tc_blob = h->d_tc16_blob;
+        fused_kernel<2, 2><<<grid, kThreads, kFusedSmemBytes, st>>>(fp, h->bias);
+      } else if (h->ffn_impl >= 1) {
+        fused_kernel<2, 1><<<grid, kThreads, kFusedSmemBytes, st>>>(fp, h->bias);
+      } else {
+        fused_kernel<2, 0><<<grid, kThreads, kFusedSmemBytes, st>>>(fp, h->par);
+      }
       break;
   }
   g_launches.fetch_add(1);
@@ -243,9 +253,11 @@ int vadb200_create(const vadb200_config* c, int device, vadb200_handle** out) {
   if (e == cudaSuccess) e = cudaMemcpy(h->d_tw, tw, sizeof(tw), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_sink, 256);
   if (e == cudaSuccess) e = cudaMalloc(&h->d_tc_blob, kTcBlobBytes);
+  if (e == cudaSuccess) e = cudaMalloc(&h->d_tc16_blob, kTc16BlobBytes);
   if (e != cudaSuccess) {
     cudaFree(h->d_tw);
     cudaFree(h->d_sink);
+    cudaFree(h->d_tc_blob);
     delete h;
     return cuda_fail(e, "vadb200_create");
   }
@@ -278,6 +290,7 @@ int vadb200_destroy(vadb200_handle* h) {
   cudaFree(h->d_tw);
   cudaFree(h->d_sink);
   cudaFree(h->d_tc_blob);
+  cudaFree(h->d_tc16_blob);
   delete h;
   return 0;
 }
@@ -305,11 +318,15 @@ int vadb200_set_ffn_weights(vadb200_handle* h, const float* W1, const float* b1,
   CU(cudaSetDevice(h->device));
   CU(cudaDeviceSynchronize());
   CU(cudaMemcpy(h->d_tc_blob, blob.data(), kTcBlobBytes, cudaMemcpyHostToDevice));
+  std::vector<unsigned char> blob16(kTc16BlobBytes);
+  h->tc16_ok = tc16_pack_weights(h->par, blob16.data(), h->bias);
+  if (h->tc16_ok) CU(cudaMemcpy(h->d_tc16_blob, blob16.data(), kTc16BlobBytes, cudaMemcpyHostToDevice));
   return 0;
 }
 
 int vadb200_set_ffn_impl(vadb200_handle* h, int impl) {
-  if (!h || impl < 0 || impl > 1) return fail(VADB200_E_INVALID, "impl must be 0 (fp32) or 1 (tcgen05 tf32x3)");
+  if (!h || impl < 0 || impl > 2)
+    return fail(VADB200_E_INVALID, "impl must be 0 (fp32), 1 (tcgen05 tf32 hi/lo) or 2 (tcgen05 fp16 hi/lo)");
   h->ffn_impl = impl;
   return 0;
 }
@@ -705,11 +722,12 @@ int vadb200_ffn_predict(vadb200_handle* h, const float* d_x, int64_t n, uint8_t*
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = ensure_tables(h);
   if (rc) return rc;
-  if (h->ffn_impl == 1) {
-    rc = ensure_attrs(h);
-    if (rc) return rc;
-    ffn_tc_rows_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, kFfnTcSmemBytes, st>>>(d_x, n, h->d_tc_blob,
-                                                                                                 d_labels, d_logits, h->bias);
+  if (h->ffn_impl >= 2 && h->tc16_ok) {
+    ffn_tc_rows_kernel<2><<<static_cast<unsigned>((n + 127) / 128), 128, kFfnTcSmemBytes, st>>>(
+        d_x, n, h->d_tc16_blob, d_labels, d_logits, h->bias);
+  } else if (h->ffn_impl >= 1) {
+    ffn_tc_rows_kernel<1><<<static_cast<unsigned>((n + 127) / 128), 128, kFfnTcSmemBytes, st>>>(
+        d_x, n, h->d_tc_blob, d_labels, d_logits, h->bias);
   } else {
     ffn_rows_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(d_x, n, d_labels, d_logits, h->par);
   }
@@ -840,7 +858,7 @@ int vadb200_synth_pcm(vadb200_handle* h, int16_t* d_out, int64_t n_utt, int64_t 
 }
 
 int vadb200_fp32_peak(vadb200_handle* h, int variant, int iters, double* tflops_out) {
-  if (!h || !tflops_out || iters < 1 || variant < 0 || variant > 1) return fail(VADB200_E_INVALID, "bad argument");
+  if (!h || !tflops_out || iters < 1 || variant < 0 || variant > 6) return fail(VADB200_E_INVALID, "bad argument");
   CU(cudaSetDevice(h->device));
   int rc = ensure_tables(h);
   if (rc) return rc;
@@ -852,13 +870,20 @@ int vadb200_fp32_peak(vadb200_handle* h, int variant, int iters, double* tflops_
   for (int rep = 0; rep < 5; ++rep) {
     CU(cudaEventRecord(e0, nullptr));
     if (variant == 0) fp32_peak_kernel<0><<<grid, 256>>>(h->d_sink, iters, 1.0000001f, 1e-9f);
-    else fp32_peak_kernel<1><<<grid, 256>>>(h->d_sink, iters, 1.0000001f, 1e-9f);
+    else if (variant == 1) fp32_peak_kernel<1><<<grid, 256>>>(h->d_sink, iters, 1.0000001f, 1e-9f);
+    else if (variant == 2) fp32x2_peak_kernel<2><<<grid, 256>>>(h->d_sink, iters, 1.0000001f, 1e-9f);
+    else if (variant == 3) fp32x2_peak_kernel<3><<<grid, 256>>>(h->d_sink, iters, 1.0000001f, 1e-9f);
+    else if (variant == 4) fp32mix_peak_kernel<8><<<grid, 256>>>(h->d_sink, iters, 1.0000001f, 1e-9f);
+    else if (variant == 5) fp32mix_peak_kernel<4><<<grid, 256>>>(h->d_sink, iters, 1.0000001f, 1e-9f);
+    else fp32mix_peak_kernel<0><<<grid, 256>>>(h->d_sink, iters, 1.0000001f, 1e-9f);
     g_launches.fetch_add(1);
     CU(cudaEventRecord(e1, nullptr));
     CU(cudaEventSynchronize(e1));
     float ms = 0.f;
     CU(cudaEventElapsedTime(&ms, e0, e1));
-    const double flops = 2.0 * 16 * 8 * static_cast<double>(iters) * 256.0 * grid;
+    const double per_rep = variant <= 1 ? 2.0 * 16 : variant <= 3 ? 4.0 * 16
+                         : variant == 4 ? 4.0 * 8 + 2.0 * 8 : variant == 5 ? 4.0 * 8 + 2.0 * 4 : 4.0 * 8;
+    const double flops = per_rep * 8 * static_cast<double>(iters) * 256.0 * grid;
     if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
   }
   cudaEventDestroy(e0);

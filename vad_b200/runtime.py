@@ -106,8 +106,10 @@ class Handle(object):
         self.has_ffn = True
 
     def set_ffn_impl(self, impl):
-        """0 / "fp32": CUDA-core FFMA; 1 / "tc": tcgen05 tensor cores (tf32 x3, TMEM accumulators)."""
-        impl = {"fp32": 0, "tc": 1}.get(impl, impl)
+        """0 / "fp32": CUDA-core FFMA; 1 / "tc": tcgen05 kind::tf32 on hi/lo operands; 2 / "tc16" (default):
+        tcgen05 kind::f16 on statically scaled fp16 hi/lo operands (half the MMAs; falls back to "tc" for
+        weights whose scales would be out of range)."""
+        impl = {"fp32": 0, "tc": 1, "tc16": 2}.get(impl, impl)
         check(self.lib.vadb200_set_ffn_impl(self._h, int(impl)))
 
     @property
