@@ -35,7 +35,7 @@ struct PairThreads {   // registers of the 16 threads of one half-warp: two fram
 
 // The fused kernel's warp_fft_quad for one half-warp: frame A at w32a, frame B `delta` words later;
 // powers go to P columns col, col + 1.
-void fft_pair_pcm(const uint32_t* w32a, int delta, float* P, int col) {
+void fft_pair_pcm(const uint32_t* w32a, int delta, float* P2, int col) {
   PairThreads th;
   std::vector<f2> ex(kExchFrame);
   for (int t = 0; t < 16; ++t) {
@@ -56,9 +56,11 @@ void fft_pair_pcm(const uint32_t* w32a, int delta, float* P, int col) {
     }
   for (int k1 = 0; k1 < 16; ++k1) {
     auto xch = [&](f2 /*mine*/, int j, bool imag, int partner) { return imag ? si[partner][j] : sr[partner][j]; };
-    auto store = [&](int bin, f2 v) {
-      P[bin * kPPitch + col] = v.x;
-      P[bin * kPPitch + col + 1] = v.y;
+    auto store = [&](int bin, f2 v) {      // the kernels' P2Store
+      if (bin >= kMelFirstBin) {
+        P2[p2_index(bin, col)] = v.x;
+        P2[p2_index(bin, col) + 2] = v.y;
+      }
     };
     fft_split_store(th.xr[k1], th.xi[k1], k1, g_tw2, xch, store);
   }
@@ -102,6 +104,8 @@ int emul_init(const float* ffn_weights) {
   std::string why;
   if (!pack_mel_weights(fb.data(), c_tab.melw, &why)) return -1;
   folded_dct(cfg, c_tab.dct);
+  pack_mel_pairs(fb.data(), c_tab.melw2);
+  pack_dct_pairs(c_tab.dct, c_tab.dctp);
   fft_twiddles(g_tw1, g_tw2);
   float* dst = g_ffn.W1;
   const size_t n = kNFeat * kH1 + kH1 + kH1 * kH2 + kH2 + kH2 * kH3 + kH3 + kH3 * kNCls + kNCls;
@@ -134,7 +138,7 @@ int emul_utterance(const int16_t* pcm, long long n_samples, int feat_mode, float
   // the ring); the emulation computes all T so the MFCC rows can be checked too.
   const int n = static_cast<int>(T);
   const int nsteps = (n + kStepFrames - 1) / kStepFrames;
-  std::vector<float> P(256 * kPPitch), logE(kNMel * 32), ring(kNCep * kRing);
+  std::vector<float> P(kP2Rows * kP2Pitch), logE(kNMel * 32), ring(kNCep * kRing);
   std::vector<int16_t> stage(kStageSamples + 8);
   int out_done = 2;
   for (int s = 0; s < nsteps; ++s) {
@@ -151,12 +155,19 @@ int emul_utterance(const int16_t* pcm, long long n_samples, int feat_mode, float
     // mel + log phase: warp g = filter group, lane = P column
     for (int g = 0; g < 8; ++g)
       for (int lane = 0; lane < 32; ++lane)
-        mel_group_dispatch<kPPitch, 32>(g, P.data() + lane, logE.data() + lane);
+        mel2_group_dispatch<kP2Pitch, 32>(g, P.data() + 2 * lane, logE.data() + lane);
     // DCT phase: warp w -> coefficients w and w + 8
-    for (int c = 0; c < kNCep; ++c)
+    for (int w = 0; w < 8; ++w)
       for (int lane = 0; lane < 32; ++lane) {
         const int f = s * kStepFrames + slot_of_col(lane);
-        ring[c * kRing + f % kRing] = dct_coef<32>(logE.data() + lane, c);
+        if (w + 8 < kNCep) {
+          float ra, rb;
+          dct_coef2<32>(logE.data() + lane, w, ra, rb);
+          ring[w * kRing + f % kRing] = ra;
+          ring[(w + 8) * kRing + f % kRing] = rb;
+        } else {
+          ring[w * kRing + f % kRing] = dct_coef<32>(logE.data() + lane, w);
+        }
       }
     const int computed = std::min((s + 1) * kStepFrames, n);
     if (mfcc_out)

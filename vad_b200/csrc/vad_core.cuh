@@ -53,9 +53,26 @@ constexpr int kH1 = 64, kH2 = 32, kH3 = 16, kNCls = 3;  // ffn_trainer.py:108-11
 // ---- parameter blocks ---------------------------------------------------------------------------
 // Mel / DCT tables depend only on the (single, compiled-in) reference configuration, so every
 // handle uploads bit-identical content: the __constant__ copy carries no per-handle state.
-struct MelDctTables {
-  float melw[448];               // 444 non-zero triangle weights x 2^-20, filter-major (kMelOff)
-  float dct[kNCep * kNMel];      // lifter[k] * dct2_ortho[k][n] * log10(2)   (input is log2 E)
+// Bin-pair form of the filterbank for the packed (FFMA2) mel stage: the power tile stores bins 2q, 2q+1 of one
+// frame side by side, filter m covers pair rows mel_q0(m) .. mel_q0(m) + mel_nq(m) - 1 and its weights are
+// stored as (w[2q], w[2q+1]) with zeros outside [kMelLo, kMelHi).
+constexpr int kP2Pitch = 66;                       // floats per pair row: 32 columns x 2 bins, + 2 (== 2 mod 32)
+constexpr int kP2FirstRow = kMelFirstBin / 2;      // bins below 10 carry no mel weight
+constexpr int kP2Rows = kBins / 2 - kP2FirstRow;   // 123
+constexpr int mel_q0(int m) { return kMelLo[m] >> 1; }
+constexpr int mel_nq(int m) { return ((kMelHi[m] - 1) >> 1) - (kMelLo[m] >> 1) + 1; }
+constexpr int mel_qoff(int m) {
+  int s = 0;
+  for (int i = 0; i < m; ++i) s += mel_nq(i);
+  return s;
+}
+constexpr int kMelPairs = mel_qoff(kNMel);
+
+struct alignas(16) MelDctTables {
+  float melw2[2 * kMelPairs + 2];  // pair weights x 2^-20, filter-major (mel_qoff); first: 16-byte aligned for LDCU.128
+  float dctp[5][kNMel][2];         // (M[p][n], M[p + 8][n]) for the two coefficients a warp owns, p = 0 .. 4
+  float melw[448];                 // 444 non-zero triangle weights x 2^-20, filter-major (kMelOff)
+  float dct[kNCep * kNMel];        // M = lifter[k] * dct2_ortho[k][n] * log10(2)   (input is log2 E)
 };
 VADB_CONSTANT MelDctTables c_tab;
 
@@ -371,6 +388,44 @@ VADB_HD void mel_group_dispatch(int g, const float* P, float* logE) {
   }
 }
 
+// Packed mel: P2 points at this lane's column of the pair tile (row r = pair row - kP2FirstRow at P2 + r * PITCH2,
+// two floats = bins 2q, 2q+1).  One LDS.64 + one FFMA2 per bin pair; the weight pair is a uniform operand.
+template <int G, int PITCH2, int OPITCH>
+VADB_HD void mel2_group(const float* P2, float* logE) {
+  static_for<0, kMelGroupCount[G]>([&](auto J) {
+    constexpr int m = kMelGroupFilter[G][J];
+    constexpr int q0 = mel_q0(m), nq = mel_nq(m), off = mel_qoff(m);
+    f2 a0 = mk2(0.0f, 0.0f), a1 = a0, a2 = a0, a3 = a0;   // four chains: dependent-FFMA2 latency / 4
+    static_for<0, nq>([&](auto Q) {
+      constexpr int q = Q;
+      const float* pp = P2 + (q0 + q - kP2FirstRow) * PITCH2;
+      const f2 pv = mk2(pp[0], pp[1]);
+      const f2 wv = mk2(c_tab.melw2[2 * (off + q)], c_tab.melw2[2 * (off + q) + 1]);
+      if constexpr ((q & 3) == 0) a0 = vfma(pv, wv, a0);
+      else if constexpr ((q & 3) == 1) a1 = vfma(pv, wv, a1);
+      else if constexpr ((q & 3) == 2) a2 = vfma(pv, wv, a2);
+      else a3 = vfma(pv, wv, a3);
+    });
+    const f2 s = vadd(vadd(a0, a2), vadd(a1, a3));
+    logE[m * OPITCH] = log2_energy(s.x + s.y);
+  });
+}
+template <int PITCH2, int OPITCH>
+VADB_HD void mel2_group_dispatch(int g, const float* P2, float* logE) {
+  switch (g) {
+    case 0: mel2_group<0, PITCH2, OPITCH>(P2, logE); break;
+    case 1: mel2_group<1, PITCH2, OPITCH>(P2, logE); break;
+    case 2: mel2_group<2, PITCH2, OPITCH>(P2, logE); break;
+    case 3: mel2_group<3, PITCH2, OPITCH>(P2, logE); break;
+    case 4: mel2_group<4, PITCH2, OPITCH>(P2, logE); break;
+    case 5: mel2_group<5, PITCH2, OPITCH>(P2, logE); break;
+    case 6: mel2_group<6, PITCH2, OPITCH>(P2, logE); break;
+    default: mel2_group<7, PITCH2, OPITCH>(P2, logE); break;
+  }
+}
+// offset (floats) of power bin `bin` of column `col` in the pair tile
+VADB_HD int p2_index(int bin, int col) { return ((bin >> 1) - kP2FirstRow) * kP2Pitch + 2 * col + (bin & 1); }
+
 // DCT-II(ortho)[:13] x lifter x log10(2) of the 26 log2-energies of one frame (column).
 template <int PITCH>
 VADB_HD float dct_coef(const float* logE, int c) {
@@ -387,24 +442,24 @@ VADB_HD float dct_coef(const float* logE, int c) {
   return (a0 + a2) + (a1 + a3);
 }
 
-// Two coefficients of the same frame at once (shares the 26 loads, 8 independent chains).
+// Coefficients p and p + 8 of the same frame at once (p = 0 .. 4): one FFMA2 per log-energy on the coefficient
+// pair, the log-energy broadcast to both halves.  Per coefficient the chains are those of dct_coef (bit-identical).
 template <int PITCH>
-VADB_HD void dct_coef2(const float* logE, int ca, int cb, float& ra, float& rb) {
-  float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f, b0 = 0.0f, b1 = 0.0f, b2 = 0.0f, b3 = 0.0f;
+VADB_HD void dct_coef2(const float* logE, int p, float& ra, float& rb) {
+  f2 a0 = mk2(0.0f, 0.0f), a1 = a0, a2 = a0, a3 = a0;
+  const float (*w)[2] = c_tab.dctp[p];
 #pragma unroll
   for (int n = 0; n < 24; n += 4) {
-    const float l0 = logE[(n + 0) * PITCH], l1 = logE[(n + 1) * PITCH], l2 = logE[(n + 2) * PITCH],
-                l3 = logE[(n + 3) * PITCH];
-    a0 = fmaf(l0, c_tab.dct[ca * kNMel + n + 0], a0); b0 = fmaf(l0, c_tab.dct[cb * kNMel + n + 0], b0);
-    a1 = fmaf(l1, c_tab.dct[ca * kNMel + n + 1], a1); b1 = fmaf(l1, c_tab.dct[cb * kNMel + n + 1], b1);
-    a2 = fmaf(l2, c_tab.dct[ca * kNMel + n + 2], a2); b2 = fmaf(l2, c_tab.dct[cb * kNMel + n + 2], b2);
-    a3 = fmaf(l3, c_tab.dct[ca * kNMel + n + 3], a3); b3 = fmaf(l3, c_tab.dct[cb * kNMel + n + 3], b3);
+    a0 = vfmas(logE[(n + 0) * PITCH], mk2(w[n + 0][0], w[n + 0][1]), a0);
+    a1 = vfmas(logE[(n + 1) * PITCH], mk2(w[n + 1][0], w[n + 1][1]), a1);
+    a2 = vfmas(logE[(n + 2) * PITCH], mk2(w[n + 2][0], w[n + 2][1]), a2);
+    a3 = vfmas(logE[(n + 3) * PITCH], mk2(w[n + 3][0], w[n + 3][1]), a3);
   }
-  const float l24 = logE[24 * PITCH], l25 = logE[25 * PITCH];
-  a0 = fmaf(l24, c_tab.dct[ca * kNMel + 24], a0); b0 = fmaf(l24, c_tab.dct[cb * kNMel + 24], b0);
-  a1 = fmaf(l25, c_tab.dct[ca * kNMel + 25], a1); b1 = fmaf(l25, c_tab.dct[cb * kNMel + 25], b1);
-  ra = (a0 + a2) + (a1 + a3);
-  rb = (b0 + b2) + (b1 + b3);
+  a0 = vfmas(logE[24 * PITCH], mk2(w[24][0], w[24][1]), a0);
+  a1 = vfmas(logE[25 * PITCH], mk2(w[25][0], w[25][1]), a1);
+  const f2 r = vadd(vadd(a0, a2), vadd(a1, a3));
+  ra = r.x;
+  rb = r.y;
 }
 
 VADB_HD float vadb_rsqrt(float v) {

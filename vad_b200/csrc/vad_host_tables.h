@@ -79,6 +79,26 @@ inline bool pack_mel_weights(const double* fb /*[26][256]*/, float* out448, std:
   return true;
 }
 
+// Pair weights of the packed mel stage: filter m, pair row q0 + q covers bins 2 (q0 + q), + 1.
+inline void pack_mel_pairs(const double* fb /*[26][256]*/, float* melw2) {
+  for (int m = 0; m < kNMel; ++m)
+    for (int q = 0; q < mel_nq(m); ++q)
+      for (int e = 0; e < 2; ++e) {
+        const int bin = 2 * (mel_q0(m) + q) + e;
+        const bool inside = bin >= kMelLo[m] && bin < kMelHi[m];
+        melw2[2 * (mel_qoff(m) + q) + e] = inside ? static_cast<float>(std::ldexp(fb[m * kBins + bin], -20)) : 0.0f;
+      }
+  melw2[2 * kMelPairs] = melw2[2 * kMelPairs + 1] = 0.0f;
+}
+// (M[p][n], M[p + 8][n]) pairs for dct_coef2
+inline void pack_dct_pairs(const float* dct /*[13][26]*/, float (*dctp)[kNMel][2]) {
+  for (int p = 0; p < 5; ++p)
+    for (int n = 0; n < kNMel; ++n) {
+      dctp[p][n][0] = dct[p * kNMel + n];
+      dctp[p][n][1] = dct[(p + 8) * kNMel + n];
+    }
+}
+
 // M[k][n] = lifter[k] * s_k * cos(pi k (2n+1) / 52) * log10(2): mfcc = M . log2(E)
 inline void folded_dct(const MfccConfig& c, float* out /*[13][26]*/) {
   const double pi = 3.14159265358979323846;

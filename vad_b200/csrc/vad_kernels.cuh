@@ -42,7 +42,8 @@ constexpr int kBlockSteps = 8;                                 // block phase ev
 constexpr int kOffPcm = 0;
 constexpr int kOffExch = kOffPcm + 2 * kStagePad * 2;                       // 21504
 constexpr int kOffP = kOffExch + kWarps * 2 * kExchFrame * 8;               // + 34816
-constexpr int kOffLogE = kOffP + kBins * kPPitch * 4;                       // + 34816
+constexpr int kP2Bytes = (kP2Rows * kP2Pitch * 4 + 15) & ~15;               // pair tile: 123 rows x 66 floats
+constexpr int kOffLogE = kOffP + kP2Bytes;                                  // + 32480
 constexpr int kOffRing = kOffLogE + kNMel * 32 * 4;                         // + 3328
 constexpr int kOffTw1 = kOffRing + ((kNCep * kRingPitch * 4 + 15) & ~15);   // + 15040
 constexpr int kOffTw2 = kOffTw1 + 256 * 8;
@@ -50,7 +51,7 @@ constexpr int kOffBar = kOffTw2 + 128 * 8;
 constexpr int kOffSeg = kOffBar + 32;                                       // 4 mbarriers: pcm x2, weights, mma
 constexpr int kFusedSmemBytes = kOffSeg + 16;                               // s_seg, s_tmem
 constexpr int kBlockStepsTc = 4;                                            // tensor-core FFN: one M=128 tile
-static_assert(kTcBlobBytes <= kWarps * 2 * kExchFrame * 8 + kBins * kPPitch * 4, "weight blob must fit exch + P");
+static_assert(kTcBlobBytes <= kWarps * 2 * kExchFrame * 8 + kP2Bytes, "weight blob must fit exch + P");
 static_assert(2 * (kFusedSmemBytes + 1024) <= 233472, "two CTAs per SM");
 
 struct Segment {
@@ -137,17 +138,16 @@ struct ShflXchg {
 
 // P-tile column of frame slot fs inside a 32-frame step.  A half-warp carries frame slots
 // 4w + h and 4w + h + 2 (so that the two half-warps' PCM reads fall on different banks) and stores
-// their powers side by side as one 64-bit word: columns 4w + 2h, 4w + 2h + 1.
+// their powers in adjacent columns 4w + 2h, 4w + 2h + 1.
 __host__ __device__ __forceinline__ int slot_of_col(int c) { return (c & ~3) | ((c >> 1) & 1) | ((c & 1) << 1); }
 
 // Four frames of a warp through the FFT: half-warp h = lanes 16h..16h+15, two frames per thread.
 // w32a: first PCM word of frame A; frame B starts `delta` words later.  ex: this half-warp's
-// transpose scratch (kExchFrame 64-bit slots).  Powers go to P columns col, col + 1.
-// Bins below FIRST are not stored (the mel filterbank starts at bin 10): s_P may then point FIRST rows
-// before a tile that holds rows FIRST .. 255 only.
-template <int NZ, int FIRST = 0>
+// transpose scratch (kExchFrame 64-bit slots).
+// store(bin, v): receives |2X|^2 of power bin `bin` for frame A (v.x) and frame B (v.y).
+template <int NZ, class STORE>
 __device__ __forceinline__ void warp_fft_quad(const uint32_t* w32a, int delta, f2* ex, const cf2* s_tw1,
-                                               const cf2* s_tw2, float* s_P, int col, int lane) {
+                                               const cf2* s_tw2, int lane, STORE&& store) {
   const int t = lane & 15;
   f2 xr[16], xi[16];
   fft_load_pcm2(w32a, delta, t, xr, xi);
@@ -161,10 +161,21 @@ __device__ __forceinline__ void warp_fft_quad(const uint32_t* w32a, int delta, f
   exch_load_plane(ex, t, xi);
   __syncwarp();
   dft16<16>(xr, xi);
-  fft_split_store(xr, xi, t, s_tw2, ShflXchg{lane}, [&](int bin, f2 v) {
-    if (FIRST == 0 || bin >= FIRST) *reinterpret_cast<f2*>(s_P + bin * kPPitch + col) = v;
-  });
+  fft_split_store(xr, xi, t, s_tw2, ShflXchg{lane}, store);
 }
+// The fused kernels' power tile: pair rows (bins 2q, 2q+1 side by side per column, vad_core.cuh p2_index); bins
+// below the first mel bin are dropped.  Columns col (frame A) and col + 1 (frame B).
+struct P2Store {
+  float* P2;
+  int col;
+  __device__ __forceinline__ void operator()(int bin, f2 v) const {
+    if (bin >= kMelFirstBin) {
+      float* q = P2 + p2_index(bin, col);
+      q[0] = v.x;
+      q[2] = v.y;
+    }
+  }
+};
 
 // Both frames of a warp (lanes 0-15 / 16-31) through the FFT; P column = frame slot fi.
 template <int NZ, class LOAD>
@@ -323,14 +334,15 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
         // half-warp h: frame slots 4 warp + h and + 2 (PCM 80 words apart per slot -> the two half-warps
         // read different banks), P columns 4 warp + 2 h, + 1
         f2* ex = reinterpret_cast<f2*>(s_exch) + (warp * 2 + h) * kExchFrame;
-        warp_fft_quad<13>(stage32 + (warp * 4 + h) * (kHop / 2), kHop, ex, s_tw1, s_tw2, s_P, warp * 4 + 2 * h, lane);
+        warp_fft_quad<13>(stage32 + (warp * 4 + h) * (kHop / 2), kHop, ex, s_tw1, s_tw2, lane,
+                          P2Store{s_P, warp * 4 + 2 * h});
       }
       __syncthreads();
 
       // ---- mel + log phase -----------------------------------------------------------------
       // (a rolled, table-driven mel loop -- one small code body for all warps, weights in shared memory -- was
       // measured 5.8 % slower than these eight straight-line regions: its loads are latency-exposed)
-      if (!(VADB_DBG(p) & 2)) mel_group_dispatch<kPPitch, 32>(warp, s_P + lane, s_logE + lane);
+      if (!(VADB_DBG(p) & 2)) mel2_group_dispatch<kP2Pitch, 32>(warp, s_P + 2 * lane, s_logE + lane);
       const int computed = min((s + 1) * kStepFrames, n);
       const bool block_now = (((s + 1) % kBlk) == 0 || s == nsteps - 1) && !(VADB_DBG(p) & 8);
       const bool tc_now = TC && block_now && (computed - 2 - out_done) > 0;  // block-uniform
@@ -347,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
         const int col = (s * kStepFrames + slot_of_col(lane)) % kRing;  // lane = P column
         if (warp + 8 < kNCep) {
           float ra, rb;
-          dct_coef2<32>(s_logE + lane, warp, warp + 8, ra, rb);
+          dct_coef2<32>(s_logE + lane, warp, ra, rb);
           s_ring[warp * kRingPitch + col] = ra;
           s_ring[(warp + 8) * kRingPitch + col] = rb;
         } else {
@@ -777,8 +789,10 @@ struct BankParams {
   int feat_mode;
 };
 constexpr int kStreamFramePitch = 416;  // samples per staged frame row (208 words == 16 mod 32)
+constexpr int kStreamPBytes = kP2Bytes > (kNFeat + kH1 + kH2 + kH3 + kNCep) * 32 * 4
+                                  ? kP2Bytes : (kNFeat + kH1 + kH2 + kH3 + kNCep) * 32 * 4;  // P tile, later activations
 constexpr int kStreamSmemBytes = kStepFrames * kStreamFramePitch * 2 + kWarps * 2 * kExchFrame * 8 +
-                                 kBins * kPPitch * 4 + kNMel * 32 * 4 + 384 * 8;
+                                 kStreamPBytes + kNMel * 32 * 4 + 384 * 8;
 
 // One CTA = 32 streams.  FFT: the fused kernel's packed two-frames-per-thread pass.  The decision
 // tail is spread over all 8 warps with lane = stream: warp w owns cepstral coefficients w, w + 8
@@ -789,7 +803,7 @@ __global__ void __launch_bounds__(kThreads) stream_feed_kernel(const BankParams 
   int16_t* s_fr = reinterpret_cast<int16_t*>(smem);
   cf2* s_exch = reinterpret_cast<cf2*>(smem + kStepFrames * kStreamFramePitch * 2);
   float* s_P = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_exch) + kWarps * 2 * kExchFrame * 8);
-  float* s_logE = s_P + kBins * kPPitch;
+  float* s_logE = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(s_P) + kStreamPBytes);
   cf2* s_tw1 = reinterpret_cast<cf2*>(s_logE + kNMel * 32);
   cf2* s_tw2 = s_tw1 + 256;
   // after the mel phase the P tile is dead: activations live there
@@ -824,10 +838,10 @@ __global__ void __launch_bounds__(kThreads) stream_feed_kernel(const BankParams 
   {
     f2* ex = reinterpret_cast<f2*>(s_exch) + (warp * 2 + h) * kExchFrame;
     const uint32_t* w32 = reinterpret_cast<const uint32_t*>(s_fr + (warp * 4 + h) * kStreamFramePitch);
-    warp_fft_quad<13>(w32, kStreamFramePitch, ex, s_tw1, s_tw2, s_P, warp * 4 + 2 * h, lane);
+    warp_fft_quad<13>(w32, kStreamFramePitch, ex, s_tw1, s_tw2, lane, P2Store{s_P, warp * 4 + 2 * h});
   }
   __syncthreads();
-  mel_group_dispatch<kPPitch, 32>(warp, s_P + lane, s_logE + lane);
+  mel2_group_dispatch<kP2Pitch, 32>(warp, s_P + 2 * lane, s_logE + lane);
   __syncthreads();
   // ---- DCT + ring + window features: warp = coefficient (w, w + 8), lane = P column ----------------
   const int slot = slot_of_col(lane);      // stream of this lane inside the CTA

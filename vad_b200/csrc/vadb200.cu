@@ -247,6 +247,8 @@ int vadb200_create(const vadb200_config* c, int device, vadb200_handle** out) {
     return fail(VADB200_E_UNSUPPORTED, why);
   }
   folded_dct(cfg, h->tab.dct);
+  pack_mel_pairs(h->fb.data(), h->tab.melw2);
+  pack_dct_pairs(h->tab.dct, h->tab.dctp);
   cf2 tw[384];
   fft_twiddles(tw, tw + 256);
   cudaError_t e = cudaMalloc(&h->d_tw, sizeof(tw));
