@@ -175,6 +175,196 @@ def workload_config(a, n, sample_note=None):
     return c
 
 
+# ----------------------------------------------------------------------------------------- helpers
+def bind_to_gpu_numa(local):
+    """Pin this rank's host threads to the CPUs of its GPU's NUMA node BEFORE any pinned allocation, so the e2e
+    staging windows are placed next to the PCIe root the GPU hangs off.  Returns a short description."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"pci": bdf, "numa_node": node, "bound": False, "why": "platform reports no NUMA affinity"}
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        n_nodes = len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")])
+        if allowed and n_nodes > 1:
+            os.sched_setaffinity(0, allowed)
+        return {"pci": bdf, "numa_node": node, "numa_nodes": n_nodes, "cpus": len(allowed),
+                "bound": bool(allowed and n_nodes > 1)}
+    except Exception as ex:  # sysfs absent (containers): keep going unbound
+        return {"bound": False, "why": str(ex)[:80]}
+
+
+def cuda_time_ms(fn, steps, warmup, torch):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def parity_sample(h, plan, pcm, labels, n_utt, L, stride, seed, first_utt, k):
+    """Outside the timed region: k utterances of the RESIDENT shard (first, last, evenly spaced) -- the device PCM
+    must equal the host generator bit for bit, and the labels the timed launches produced must equal the oracle's
+    on every decisive row; a small re-run of the same utterances with logits checks the logit tolerance."""
+    import numpy as np
+    from oracle import ref_math as rm
+    from vad_b200 import batch, runtime
+    from vad_b200.synth import synth_utterance
+    w = runtime.glorot_ffn(0)
+    idx = sorted(set(int(round(i * (n_utt - 1) / max(k - 1, 1))) for i in range(k)))
+    ro = plan.row_offsets
+    ok_pcm = ok_lab = ok_logit = True
+    max_err = 0.0
+    sub = []
+    for u in idx:
+        host = synth_utterance(seed, first_utt + u, L)
+        dev = pcm[u * stride:u * stride + L].cpu().numpy()
+        ok_pcm &= bool(np.array_equal(host, dev))
+        sub.append(host)
+        _, feats, ref_logits, ref_labels = rm.vad_utterance(host, w)
+        got = labels[int(ro[u]):int(ro[u + 1])].cpu().numpy()
+        fin = np.isfinite(feats).all(axis=1)
+        srt = np.sort(ref_logits[fin], axis=1)
+        dec = (srt[:, -1] - srt[:, -2]) > 2 * (1e-3 + 1e-3 * np.abs(srt[:, -1]))
+        ok_lab &= bool(np.array_equal(got[fin][dec], ref_labels[fin][dec]) and np.all(got[~fin] == 0))
+    la, lo = batch.vad_batch(sub, handle=h, want_logits=True)
+    for host, lg in zip(sub, lo):
+        _, feats, ref_logits, _ = rm.vad_utterance(host, w)
+        fin = np.isfinite(feats).all(axis=1)
+        err = np.abs(lg.cpu().numpy()[fin] - ref_logits[fin])
+        max_err = max(max_err, float(err.max()) if err.size else 0.0)
+        ok_logit &= bool(np.all(err <= 1e-3 + 1e-3 * np.abs(ref_logits[fin])))
+    return {"result": "pass" if (ok_pcm and ok_lab and ok_logit) else "fail", "utterances": idx,
+            "pcm_bit_identical_to_host_generator": ok_pcm, "labels_equal_oracle_on_decisive_rows": ok_lab,
+            "logits_within_1e-3": ok_logit, "max_logit_abs_err": max_err,
+            "oracle": "oracle/ref_math.py (float64 restatement pinned to the reference's golden vectors)"}
+
+
+def stream_record(h, a, torch):
+    """configs[3]: a.streams concurrent 16 kHz streams in 10 ms chunks through analyser.StreamBank (one CUDA-graph
+    launch per tick: H2D of the chunks, stream_feed_kernel, D2H of the labels).  Latency = host wall clock from
+    'chunk batch is in pinned host memory' to 'labels are readable on the host', per tick."""
+    import numpy as np
+    from vad_b200.analyser import StreamBank
+    bank = StreamBank(a.streams, handle=h)
+    rng = np.random.default_rng(0)
+    pool = torch.from_numpy((rng.standard_normal((32, a.streams, 160)) * 3000).astype(np.int16))
+    warm = 100
+    lat = np.zeros(a.stream_ticks)
+    speech = 0
+    for t in range(warm + a.stream_ticks):
+        bank.h_chunks.copy_(pool[t % 32])            # the tick's audio arrives in pinned memory
+        t0 = time.perf_counter()
+        labels = bank.feed_pinned()
+        dt = time.perf_counter() - t0
+        if t >= warm:
+            lat[t - warm] = dt
+            speech += int((labels == 1).sum())
+    ms = np.sort(lat) * 1e3
+    p99 = float(ms[int(len(ms) * 0.99)])
+    return {"metric": "stream_chunk_latency_ms", "streams": a.streams, "ticks": a.stream_ticks, "warmup_ticks": warm,
+            "chunk_ms": 10.0, "cuda_graph": bool(bank.use_graph and bank._graphs), "launches_per_tick": 1,
+            "p50_ms": float(ms[len(ms) // 2]), "p99_ms": p99, "max_ms": float(ms[-1]), "mean_ms": float(ms.mean()),
+            "keeps_up_with_realtime": bool(p99 < 10.0), "realtime_headroom_at_p99": 10.0 / p99,
+            "audio_s_per_s_at_mean": float(a.streams * 0.010 / (ms.mean() * 1e-3)), "speech_decisions": speech,
+            "algorithmic_lag_frames": 3, "h2d_bytes_per_tick": a.streams * 320, "d2h_bytes_per_tick": a.streams,
+            "timing": "host wall clock around StreamBank.feed_pinned() (graph launch + stream sync), rank 0"}
+
+
+def analyser_record(h, torch):
+    """FusedAnalyser.feed_frame (the single-stream SKLearnAnalyzer drop-in): p50 / p99 per call."""
+    import numpy as np
+    from vad_b200.analyser import FusedAnalyser
+    from vad_b200.synth import synth_utterance
+    an = FusedAnalyser(handle=h)
+    pcm = synth_utterance(5, 0, 400 * 1205).astype(np.float32).reshape(1205, 400)
+    an.load_init_inactive_frames(list(pcm[:5]))
+    lat = []
+    for i in range(1205):
+        t0 = time.perf_counter()
+        an.feed_frame(pcm[i])
+        dt = time.perf_counter() - t0
+        if i >= 205:
+            lat.append(dt)
+    ms = np.sort(np.array(lat)) * 1e3
+    return {"calls": len(lat), "p50_ms": float(ms[len(ms) // 2]), "p99_ms": float(ms[int(len(ms) * 0.99)]),
+            "max_ms": float(ms[-1]), "frame_ms": 25.0,
+            "note": "per call: one MFCC-frame launch, one window-classify launch, one D2H sync"}
+
+
+def cfg2_record(h, peak, hbm_peak, torch):
+    """configs[1]: MFCC-only, 1024 x 10 s (327.68 MB in, 53.1 MB out; inputs larger than L2)."""
+    from vad_b200 import batch, runtime
+    n_utt, L = 1024, 160000
+    off, ln, stride = batch.uniform_layout(n_utt, L)
+    pcm = h.synth_pcm(n_utt, L, seed=0, first_utt=0, utt_stride=stride)
+    plan = runtime.Plan(h, off, ln, runtime.MODE_MFCC)
+    out = torch.empty((plan.total_rows, 13), dtype=torch.float32, device=h.device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=h.device)
+    for _ in range(3):
+        plan.mfcc(pcm, out=out)
+    tot = 0.0
+    for _ in range(10):
+        flush.fill_(1)                                 # evict the input's tail from the 126 MB L2
+        tot += cuda_time_ms(lambda: plan.mfcc(pcm, out=out), 1, 0, torch)
+    ms = tot / 10
+    frames = plan.total_rows
+    ach = frames * FLOP_PER_FRAME_MFCC / (ms * 1e-3) / 1e12
+    gbs = frames * (320 + 52) / (ms * 1e-3) / 1e9
+    return {"workload": "cfg2: MFCC-only, 1024 x 10 s utterances", "value": n_utt * 10.0 / (ms * 1e-3), "unit": UNIT,
+            "ms_per_step": ms, "frames": int(frames), "segment_frames": plan.segment_frames,
+            "l2": "256 MB flush buffer written between timed launches",
+            "roofline": {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                         "kernel": "fused_kernel<0,0>", "algorithmic_flop_per_frame": FLOP_PER_FRAME_MFCC,
+                         "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                 "algorithmic_bytes_per_frame": 372}}}
+
+
+def cfg5_record(h, peak, hbm_peak, torch):
+    """configs[4]: 8192 ragged 2-30 s utterances (seed 7), deltas + delta-deltas (39-dim rows), packed offsets."""
+    import numpy as np
+    from vad_b200 import runtime
+    n_utt, smax = 8192, 480000
+    rng = np.random.default_rng(7)
+    lens = rng.integers(32000, smax + 1, size=n_utt).astype(np.int64)
+    off = np.arange(n_utt, dtype=np.int64) * smax                 # 8-sample-aligned offsets (gaps are never read)
+    pcm = h.synth_pcm(n_utt, smax, seed=7, first_utt=0, utt_stride=smax)
+    dplan = runtime.Plan(h, off, lens, runtime.MODE_DATASET)
+    vplan = runtime.Plan(h, off, lens, runtime.MODE_VAD)
+    rows = torch.empty((dplan.total_rows, 39), dtype=torch.float32, device=h.device)
+    labels = torch.empty((vplan.total_rows,), dtype=torch.uint8, device=h.device)
+    ms_rows = cuda_time_ms(lambda: dplan.mfcc(pcm, out=rows), 5, 3, torch)
+    ms_vad = cuda_time_ms(lambda: vplan.vad(pcm, labels=labels), 5, 3, torch)
+    audio_s = float(lens.sum()) / 16000.0
+    fr = dplan.total_rows
+    ach = fr * (FLOP_PER_FRAME_MFCC + 39) / (ms_rows * 1e-3) / 1e12
+    gbs = fr * (320 + 156) / (ms_rows * 1e-3) / 1e9
+    achv = fr * FLOP_PER_FRAME_FUSED / (ms_vad * 1e-3) / 1e12
+    return {"workload": "cfg5: 8192 ragged utterances, 2-30 s uniform (seed 7), 39-dim dataset rows, packed",
+            "audio_hours": audio_s / 3600.0, "rows": int(fr), "segment_frames": dplan.segment_frames,
+            "value": audio_s / (ms_rows * 1e-3), "unit": UNIT, "ms_per_step": ms_rows,
+            "l2": "inputs larger than L2 (4.2 GB of PCM read per launch)",
+            "roofline": {"bound": "fp32", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                         "kernel": "fused_kernel<1,0>", "algorithmic_flop_per_frame": FLOP_PER_FRAME_MFCC + 39,
+                         "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                 "algorithmic_bytes_per_frame": 476}},
+            "vad": {"value": audio_s / (ms_vad * 1e-3), "unit": UNIT, "ms_per_step": ms_vad,
+                    "roofline_frac": achv / peak}}
+
+
 # ----------------------------------------------------------------------------------------- GPU arm
 def main():
     a = parse_args()
@@ -193,6 +383,7 @@ def main():
         raise SystemExit("bench.py needs CUDA devices (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -266,6 +457,9 @@ def main():
     total_audio = sum_over_ranks(audio_s)
     value = total_audio / (ms_per_step * 1e-3)
     speech_frac = float(labels[: min(frames, 50_000_000)].float().mean().item())
+    parity = None
+    if rank == 0 and a.parity_utts > 0:
+        parity = parity_sample(h, plan, pcm, labels, n_utt, L, stride, a.seed, rank * n_utt, a.parity_utts)
 
     # ---- end to end through the host-buffer C-ABI entry point ---------------------------------------
     e2e = None
@@ -291,11 +485,30 @@ def main():
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0)
         barrier()
+        # the host's concurrent H2D ceiling: every rank copies its pinned window, no kernel, between barriers
+        d_win = torch.empty(win * stride + 8, dtype=torch.int16, device=dev)
+        d_win.copy_(h_pcm, non_blocking=True)
+        torch.cuda.synchronize()
+        barrier()
+        t0c = time.perf_counter()
+        reps = 8
+        for _ in range(reps):
+            d_win.copy_(h_pcm, non_blocking=True)
+        torch.cuda.synchronize()
+        dtc = max_over_ranks(time.perf_counter() - t0c)
+        barrier()
+        ceil_gbs = sum_over_ranks(reps * h_pcm.numel() * 2) / dtc / 1e9
+        del d_win
+        e2e_gbs = sum_over_ranks(n_win * win * stride * 2) * a.e2e_steps / dt / 1e9
         e2e = {"value": total_audio * a.e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(sum_over_ranks(n_win * win * stride * 2)),
                "d2h_bytes_per_step": int(sum_over_ranks(n_win * wplan.total_rows)),
                "ms_per_step": 1e3 * dt / a.e2e_steps, "timing": "host wall clock around blocking C-ABI calls, max over ranks",
-               "host_window_bytes": int(win * stride * 2), "windows_per_step": n_win, "labels_match_device_path": same}
+               "host_window_bytes": int(win * stride * 2), "windows_per_step": n_win, "labels_match_device_path": same,
+               "h2d_GBps": e2e_gbs, "h2d_ceiling_GBps": ceil_gbs, "frac_of_h2d_ceiling": e2e_gbs / ceil_gbs,
+               "h2d_ceiling_note": "all %d ranks copying their pinned 1.92 GB window concurrently, no kernel "
+                                   "(the e2e roofline of this host at this N)" % world,
+               "numa": numa}
 
     if rank != 0:
         if world > 1:
@@ -305,9 +518,11 @@ def main():
     # ---- roofline of the dominant (only) kernel -----------------------------------------------------
     peak_reg = h.fp32_peak(0, 2048)
     peak_const = h.fp32_peak(1, 2048)
-    peak = max(peak_reg, peak_const)
-    peak_src = "live FFMA microbenchmark on this GPU (vadb200_fp32_peak: reg %.1f / const-operand %.1f TFLOP/s); " \
-               "MEASURED_PEAKS.json has no FP32 figure" % (peak_reg, peak_const)
+    peak_x2 = h.fp32_peak(2, 2048)
+    peak = max(peak_reg, peak_const, peak_x2)   # the largest of the three is the denominator
+    peak_src = "live FMA microbenchmark on this GPU (vadb200_fp32_peak: FFMA reg %.1f / FFMA const-operand %.1f / " \
+               "packed FFMA2 %.1f TFLOP/s; the maximum is used); MEASURED_PEAKS.json has no FP32 figure" % (
+                   peak_reg, peak_const, peak_x2)
     if not peak or peak <= 0:
         peak, peak_src = FP32_NOMINAL_TFLOPS, "nominal fallback 148x128x2x1.965 GHz"
     hbm_peak = None
@@ -341,12 +556,26 @@ def main():
         utts = a.cpu_utts_per_core * cores
         try:
             r = run_cpu_port(utts, cores, 1, 1, a.utt_seconds, a.seed)
-            cpu = {"value": r["audio_s_per_s"], "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "%d x %.0f s utterances of the same synthetic workload (%.0f audio-s), "
-                             "oracle/ref_loop.py under multiprocessing.Pool(%d)" % (utts, a.utt_seconds,
-                                                                                     utts * a.utt_seconds, cores)}
+            kind = r.get("kind", "port")
+            cpu = {"value": r["audio_s_per_s"], "unit": UNIT, "cores": cores, "kind": kind,
+                   "sample": "%d x %.0f s utterances of the same synthetic workload (%.0f audio-s) under "
+                             "multiprocessing.Pool(%d)%s" % (utts, a.utt_seconds, utts * a.utt_seconds, cores,
+                                                             CPU_KIND_NOTE[kind])}
         except Exception as ex:  # the GPU numbers stand on their own
             cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "port", "sample": "failed: %s" % ex}
+
+    # ---- the other configs of BASELINE.json, each with its own roofline (rank 0, after every timed region) ----
+    extra = {}
+    if not a.no_extra_configs:
+        del pcm, labels
+        torch.cuda.empty_cache()
+        try:
+            extra["stream"] = stream_record(h, a, torch)
+            extra["analyser_feed_frame"] = analyser_record(h, torch)
+            extra["cfg2"] = cfg2_record(h, peak, hbm_peak, torch)
+            extra["cfg5"] = cfg5_record(h, peak, hbm_peak, torch)
+        except Exception as ex:  # the headline line stands on its own
+            extra["error"] = repr(ex)[:300]
 
     clocks = sampler.summary(t_w0, t_w1) if sampler else None
     line = {
@@ -356,6 +585,8 @@ def main():
                 "random-init FFN weights)",
         "config": workload_config(a, world), "e2e": e2e, "gpu_launches": int(sum_over_ranks(launches)) if world == 1 else int(launches * world),
         "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "parity_sample": parity, "stream": extra.get("stream"), "analyser_feed_frame": extra.get("analyser_feed_frame"),
+        "cfg2": extra.get("cfg2"), "cfg5": extra.get("cfg5"), "extra_error": extra.get("error"),
         "frames_per_step": int(frames * world), "speech_fraction": speech_frac, "ffn_impl": a.ffn_impl,
         "gpu": torch.cuda.get_device_name(local),
     }

@@ -136,12 +136,14 @@ class StreamBank(object):
     frames earlier (the reference's feed_frame timing), or 255 while a stream's ring is filling.
     Chunk j completes frame j-2 (= 400 samples ending 80 samples into chunk j).  Per-stream state
     (320-sample history, 5-row MFCC ring) lives on the device; chunk input and label output go
-    through pinned host buffers.  A tick (H2D of the chunks, the feed kernel, D2H of the labels)
-    is captured once into a CUDA graph and replayed: one graph launch per tick."""
+    through pinned host buffers.  A tick is captured once into a CUDA graph and replayed: one graph
+    launch per tick.  With ``zero_copy`` (default) the graph is the feed kernel alone: it reads the
+    chunks from, and writes the labels to, the pinned host buffers directly over PCIe (each chunk
+    sample is read once), which removes the two copy nodes and their scheduling gaps from the tick."""
 
     NOT_READY = 255
 
-    def __init__(self, n_streams, ffn_weights=None, handle=None, use_graph=True):
+    def __init__(self, n_streams, ffn_weights=None, handle=None, use_graph=True, zero_copy=True):
         self.handle = _handle_for(ffn_weights, handle)
         if not self.handle.has_ffn:
             raise RuntimeError("StreamBank needs FFN weights")
@@ -156,6 +158,7 @@ class StreamBank(object):
         self.d_logits = torch.zeros((self.n, 3), dtype=torch.float32, device=dev)
         self.stream = torch.cuda.Stream(device=dev)
         self.use_graph = bool(use_graph)
+        self.zero_copy = bool(zero_copy)
         self._graphs = {}
 
     def reset(self):
@@ -163,6 +166,10 @@ class StreamBank(object):
         torch.cuda.synchronize(self.handle.device)
 
     def _enqueue(self, want_logits):
+        if self.zero_copy:   # pinned host memory is device-visible under UVA: no copy nodes
+            self.bank.feed_ptr(self.h_chunks.data_ptr(), self.h_labels.data_ptr(),
+                               self.h_logits.data_ptr() if want_logits else 0)
+            return
         self.d_chunks.copy_(self.h_chunks, non_blocking=True)
         self.bank.feed_ptr(self.d_chunks.data_ptr(), self.d_labels.data_ptr(),
                            self.d_logits.data_ptr() if want_logits else 0)
@@ -171,7 +178,7 @@ class StreamBank(object):
             self.h_logits.copy_(self.d_logits, non_blocking=True)
 
     def _tick(self, want_logits):
-        """One H2D + kernel + D2H on ``self.stream``; returns after the labels are on the host."""
+        """One H2D + kernel + D2H; returns after the labels are on the host."""
         if self.use_graph:
             g = self._graphs.get(want_logits)
             if g is None:  # capture once (capturing does not execute: no chunk is consumed)
@@ -179,12 +186,12 @@ class StreamBank(object):
                 with torch.cuda.graph(g, stream=self.stream):
                     self._enqueue(want_logits)
                 self._graphs[want_logits] = g
-            with torch.cuda.stream(self.stream):
-                g.replay()
+            g.replay()                                   # one cudaGraphLaunch on the caller's current stream
+            torch.cuda.current_stream(self.handle.device).synchronize()
         else:
             with torch.cuda.stream(self.stream):
                 self._enqueue(want_logits)
-        self.stream.synchronize()
+            self.stream.synchronize()
 
     def feed(self, chunks, want_logits=False):
         """chunks: array-like int16 [n, 160] on the host.  Blocks until labels are on the host."""

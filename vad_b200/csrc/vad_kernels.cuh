@@ -788,7 +788,7 @@ struct BankParams {
   const cf2* tw2;
   int feat_mode;
 };
-constexpr int kStreamFramePitch = 416;  // samples per staged frame row (208 words == 16 mod 32)
+constexpr int kStreamFramePitch = 480;  // samples per staged row: [history 320 | chunk 160] (240 words == 16 mod 32)
 constexpr int kStreamPBytes = kP2Bytes > (kNFeat + kH1 + kH2 + kH3 + kNCep) * 32 * 4
                                   ? kP2Bytes : (kNFeat + kH1 + kH2 + kH3 + kNCep) * 32 * 4;  // P tile, later activations
 constexpr int kStreamSmemBytes = kStepFrames * kStreamFramePitch * 2 + kWarps * 2 * kExchFrame * 8 +
@@ -816,24 +816,23 @@ __global__ void __launch_bounds__(kThreads) stream_feed_kernel(const BankParams 
   const int s0 = blockIdx.x * kStepFrames;
   s_tw1[tid] = p.tw1[tid];
   if (tid < 128) s_tw2[tid] = p.tw2[tid];
-  // stage frames: [hist 320 | chunk 80] per stream, then roll the history in global memory
-  for (int j = tid; j < kStepFrames * 200; j += kThreads) {  // 32-bit words: 160 hist + 40 chunk per stream
-    const int fi = j / 200, wd = j - fi * 200;
+  // stage [hist 320 | chunk 160] per stream: every chunk sample is read exactly once (the chunks may live in
+  // pinned host memory: zero-copy ticks), then roll the history in global memory from the staged copy
+  for (int j = tid; j < kStepFrames * 240; j += kThreads) {  // 32-bit words: 160 hist + 80 chunk per stream
+    const int fi = j / 240, wd = j - fi * 240;
     const int st = min(s0 + fi, p.n_streams - 1);
     const uint32_t v = (wd < 160) ? reinterpret_cast<const uint32_t*>(p.hist + static_cast<long long>(st) * 320)[wd]
                                   : reinterpret_cast<const uint32_t*>(p.chunks + static_cast<long long>(st) * 160)[wd - 160];
     reinterpret_cast<uint32_t*>(s_fr + fi * kStreamFramePitch)[wd] = v;
   }
   __syncthreads();
-  // new history = old hist[160:320] ++ chunk[0:160]
+  // new history = old hist[160:320] ++ chunk[0:160] = staged words 80 .. 239
   for (int j = tid; j < kStepFrames * 160; j += kThreads) {
     const int fi = j / 160, wd = j - fi * 160;
     const int st = s0 + fi;
-    if (st < p.n_streams) {
-      const uint32_t v = (wd < 80) ? reinterpret_cast<const uint32_t*>(s_fr + fi * kStreamFramePitch)[80 + wd]
-                                   : reinterpret_cast<const uint32_t*>(p.chunks + static_cast<long long>(st) * 160)[wd - 80];
-      reinterpret_cast<uint32_t*>(p.hist + static_cast<long long>(st) * 320)[wd] = v;
-    }
+    if (st < p.n_streams)
+      reinterpret_cast<uint32_t*>(p.hist + static_cast<long long>(st) * 320)[wd] =
+          reinterpret_cast<const uint32_t*>(s_fr + fi * kStreamFramePitch)[80 + wd];
   }
   {
     f2* ex = reinterpret_cast<f2*>(s_exch) + (warp * 2 + h) * kExchFrame;
