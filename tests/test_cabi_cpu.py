@@ -111,20 +111,6 @@ def test_synth_matches_itself_and_is_int16():
     assert 500 < big.std() < 5000 and np.abs(big).max() <= 32767
 
 
-def test_sph_reader_roundtrip(tmp_path):
-    from vad_b200.io import read_sph
-    data = (np.arange(-3000, 3000, 7)).astype(np.int16)
-    head = ("NIST_1A\n   1024\nsample_count -i %d\nsample_n_bytes -i 2\nchannel_count -i 1\n"
-            "sample_byte_format -s2 10\nsample_rate -i 16000\nsample_coding -s3 pcm\nend_head\n" % len(data)).encode()
-    path = tmp_path / "x.sph"
-    path.write_bytes(head + b" " * (1024 - len(head)) + data.astype(">i2").tobytes())
-    rate, got = read_sph(str(path))
-    assert rate == 16000 and np.array_equal(got, data)
-    (tmp_path / "bad.sph").write_bytes(b"RIFFxxxx")
-    with pytest.raises(ValueError):
-        read_sph(str(tmp_path / "bad.sph"))
-
-
 def test_shard_balanced_property():
     from hypothesis import given, settings, strategies as st
     from vad_b200 import shard

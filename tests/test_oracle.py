@@ -166,3 +166,31 @@ def test_live_reference_when_mounted():
         frame = np.clip(rng.standard_normal(400) * amp, -32768, 32767).astype(np.int16)
         np.testing.assert_allclose(rm.get_mfcc(frame, fb), ref.mfcc.get_mfcc(frame, ref.FFT_N, fb, 13),
                                    rtol=0, atol=2e-5)
+
+
+def test_ref_io_wav_path_matches_live_process_file_when_mounted(tmp_path):
+    """oracle/ref_io.py's file path (wav read + dataset rows) against the unmodified reference process_file."""
+    if not reference_shim.available():
+        pytest.skip("reference not mounted")
+    from scipy.io import wavfile
+    from oracle import ref_io
+    from vad_b200.synth import synth_utterance
+    ref = reference_shim.load()
+    pcm = synth_utterance(5, 3, 20000)
+    path = str(tmp_path / "u.wav")
+    wavfile.write(path, 16000, pcm)
+
+    class Q(object):
+        v = 0
+
+        def get(self):
+            return self.v
+
+        def put(self, v):
+            self.v = v
+
+    fb = ref.mfcc.get_mel_filterbanks(300, 8000, ref.FFT_N, 26, 16000)
+    feats = ref.file_processing.process_file([path, 400, 160, ref.FFT_N, fb, 13, Q(), None])
+    want = np.array([np.concatenate(f) for f in feats])
+    got = rm.dataset_features(rm.mfcc_utterance(ref_io.file_samples(path)))
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-5)
