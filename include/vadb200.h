@@ -46,6 +46,7 @@ extern "C" {
 typedef struct vadb200_handle vadb200_handle;
 typedef struct vadb200_plan vadb200_plan;
 typedef struct vadb200_bank vadb200_bank;
+typedef struct vadb200_trainer vadb200_trainer;
 
 /* config.py:20-27.  Only the reference values are accepted by the fused kernels. */
 typedef struct vadb200_config {
@@ -184,6 +185,25 @@ int vadb200_stream_bank_reset(vadb200_bank* b, void* stream);
 int vadb200_stream_feed(vadb200_bank* b, const int16_t* d_chunks /* [n][160], device-visible */,
                         uint8_t* d_labels /* [n], device-visible */, float* d_logits /* nullable */,
                         void* stream);
+
+/* ---- FFN training (learning/ffn_trainer.py:104-175) ---------------------------------------
+ * model.compile(loss='categorical_crossentropy', optimizer='adadelta') + model.train_on_batch for the
+ * 39-64-32-16-3 network: forward, backward and the Adadelta update as two hand-written kernels per step,
+ * deterministic (per-CTA partial gradients summed in a fixed order).  Keras-1 defaults: lr 1.0, rho 0.95,
+ * eps 1e-8.  A trainer starts from the handle's weights if set (else zeros: call _set_weights); rows
+ * d_x [n][39] float32 are what the fused kernels emit (MODE_DATASET rows after vadb200_scale_rows),
+ * d_y [n] class ids 0 / 1 / 2 (config.py:45-47).  h_loss (nullable) receives the batch loss before the
+ * update, as Keras reports it, and makes the call synchronise `stream`. */
+int vadb200_trainer_create(vadb200_handle* h, int64_t max_batch, float lr, float rho, float eps,
+                           vadb200_trainer** out);
+int vadb200_trainer_destroy(vadb200_trainer* t);
+int vadb200_trainer_set_weights(vadb200_trainer* t, const float* W1, const float* b1, const float* W2,
+                                const float* b2, const float* W3, const float* b3, const float* W4,
+                                const float* b4, int reset_optimizer);
+int vadb200_trainer_get_weights(vadb200_trainer* t, float* W1, float* b1, float* W2, float* b2, float* W3,
+                                float* b3, float* W4, float* b4);
+int vadb200_train_on_batch(vadb200_trainer* t, const float* d_x, const uint8_t* d_y, int64_t n,
+                           float* h_loss, void* stream);
 
 /* ---- bench support -------------------------------------------------------------------------
  * Counter-based integer synthetic PCM, bit-identical to vad_b200/synth.py. */

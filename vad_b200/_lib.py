@@ -60,6 +60,11 @@ SIGNATURES = {
     "vadb200_stream_bank_destroy": (C.c_int, [_P]),
     "vadb200_stream_bank_reset": (C.c_int, [_P, _P]),
     "vadb200_stream_feed": (C.c_int, [_P, _P, _P, _P, _P]),
+    "vadb200_trainer_create": (C.c_int, [_P, _I64, C.c_float, C.c_float, C.c_float, C.POINTER(_P)]),
+    "vadb200_trainer_destroy": (C.c_int, [_P]),
+    "vadb200_trainer_set_weights": (C.c_int, [_P] + [_P] * 8 + [C.c_int]),
+    "vadb200_trainer_get_weights": (C.c_int, [_P] + [_P] * 8),
+    "vadb200_train_on_batch": (C.c_int, [_P, _P, _P, _I64, _P, _P]),
     "vadb200_synth_pcm": (C.c_int, [_P, _P, _I64, _I64, _I64, C.c_uint32, _I64, _P]),
     "vadb200_fp32_peak": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "vadb200_launch_count": (_I64, []),

@@ -19,6 +19,7 @@
 
 #include "vad_host_tables.h"
 #include "vad_kernels.cuh"
+#include "ffn_train.cuh"
 
 using namespace vadb;
 
@@ -92,6 +93,16 @@ struct vadb200_plan {
   std::atomic<unsigned> launch_seq{0};
   long long total_rows = 0;
   long long seg_frames = 0;
+};
+
+struct vadb200_trainer {
+  vadb200_handle* h = nullptr;
+  long long max_batch = 0;
+  float lr = 1.0f, rho = 0.95f, eps = 1e-8f;
+  float* d_state = nullptr;    // params | acc_g | acc_u   (3 x kNParams)
+  float* d_partial = nullptr;  // [ceil(max_batch / 128)][kNParams + 1]
+  float* d_loss = nullptr;
+  long long steps = 0;
 };
 
 struct vadb200_bank {
@@ -844,6 +855,91 @@ int vadb200_exp_fft(vadb200_plan* p, const int16_t* d_pcm, int64_t pcm_len, int 
   return 0;
 }
 #endif
+
+// ---- FFN training (learning/ffn_trainer.py:104-175) --------------------------------------------------------
+int vadb200_trainer_create(vadb200_handle* h, int64_t max_batch, float lr, float rho, float eps, vadb200_trainer** out) {
+  if (!h || !out || max_batch < 1) return fail(VADB200_E_INVALID, "bad argument");
+  *out = nullptr;
+  CU(cudaSetDevice(h->device));
+  vadb200_trainer* t = new (std::nothrow) vadb200_trainer();
+  if (!t) return fail(VADB200_E_NOMEM, "host allocation failed");
+  t->h = h; t->max_batch = max_batch; t->lr = lr; t->rho = rho; t->eps = eps;
+  const long long n_part = (max_batch + kTrainRows - 1) / kTrainRows;
+  cudaError_t e = cudaMalloc(&t->d_state, 3 * kNParams * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemset(t->d_state, 0, 3 * kNParams * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&t->d_partial, n_part * (kNParams + 1) * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&t->d_loss, sizeof(float));
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute(ffn_train_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrainSmemBytes);
+  if (e != cudaSuccess) {
+    cudaFree(t->d_state); cudaFree(t->d_partial); cudaFree(t->d_loss);
+    delete t;
+    return cuda_fail(e, "vadb200_trainer_create");
+  }
+  if (h->have_ffn) {  // start from the handle's classifier
+    static_assert(sizeof(FfnParams) >= kNParams * sizeof(float), "FfnParams is the parameter vector");
+    CU(cudaMemcpy(t->d_state, &h->par, kNParams * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  *out = t;
+  return 0;
+}
+
+int vadb200_trainer_destroy(vadb200_trainer* t) {
+  if (!t) return 0;
+  cudaSetDevice(t->h->device);
+  cudaFree(t->d_state); cudaFree(t->d_partial); cudaFree(t->d_loss);
+  delete t;
+  return 0;
+}
+
+int vadb200_trainer_set_weights(vadb200_trainer* t, const float* W1, const float* b1, const float* W2, const float* b2,
+                                const float* W3, const float* b3, const float* W4, const float* b4, int reset_optimizer) {
+  if (!t || !W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !W4 || !b4) return fail(VADB200_E_INVALID, "null argument");
+  std::vector<float> v(kNParams);
+  const float* src[8] = {W1, b1, W2, b2, W3, b3, W4, b4};
+  const int off[9] = {kOffW1, kOffB1, kOffW2, kOffB2, kOffW3, kOffB3, kOffW4, kOffB4, kNParams};
+  for (int i = 0; i < 8; ++i) std::memcpy(v.data() + off[i], src[i], (off[i + 1] - off[i]) * sizeof(float));
+  CU(cudaSetDevice(t->h->device));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(t->d_state, v.data(), kNParams * sizeof(float), cudaMemcpyHostToDevice));
+  if (reset_optimizer) CU(cudaMemset(t->d_state + kNParams, 0, 2 * kNParams * sizeof(float)));
+  return 0;
+}
+
+int vadb200_trainer_get_weights(vadb200_trainer* t, float* W1, float* b1, float* W2, float* b2, float* W3, float* b3,
+                                float* W4, float* b4) {
+  if (!t || !W1 || !b1 || !W2 || !b2 || !W3 || !b3 || !W4 || !b4) return fail(VADB200_E_INVALID, "null argument");
+  std::vector<float> v(kNParams);
+  CU(cudaSetDevice(t->h->device));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(v.data(), t->d_state, kNParams * sizeof(float), cudaMemcpyDeviceToHost));
+  float* dst[8] = {W1, b1, W2, b2, W3, b3, W4, b4};
+  const int off[9] = {kOffW1, kOffB1, kOffW2, kOffB2, kOffW3, kOffB3, kOffW4, kOffB4, kNParams};
+  for (int i = 0; i < 8; ++i) std::memcpy(dst[i], v.data() + off[i], (off[i + 1] - off[i]) * sizeof(float));
+  return 0;
+}
+
+int vadb200_train_on_batch(vadb200_trainer* t, const float* d_x, const uint8_t* d_y, int64_t n, float* h_loss,
+                           void* stream) {
+  if (!t || n < 1 || !d_x || !d_y) return fail(VADB200_E_INVALID, "bad argument");
+  if (n > t->max_batch) return fail(VADB200_E_INVALID, "batch larger than the trainer's max_batch");
+  CU(cudaSetDevice(t->h->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n_part = static_cast<int>((n + kTrainRows - 1) / kTrainRows);
+  ffn_train_grad_kernel<<<n_part, kTrainRows, kTrainSmemBytes, st>>>(t->d_state, d_x, d_y, n, 1.0f / static_cast<float>(n),
+                                                                      t->d_partial);
+  ffn_train_update_kernel<<<(kNParams + 1 + 255) / 256, 256, 0, st>>>(t->d_state, t->d_state + kNParams,
+                                                                       t->d_state + 2 * kNParams, t->d_partial, n_part,
+                                                                       t->lr, t->rho, t->eps, t->d_loss);
+  g_launches.fetch_add(2);
+  CU(cudaGetLastError());
+  ++t->steps;
+  if (h_loss) {
+    CU(cudaMemcpyAsync(h_loss, t->d_loss, sizeof(float), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+  }
+  return 0;
+}
 
 // ---- bench support -----------------------------------------------------------------------------------------
 int vadb200_synth_pcm(vadb200_handle* h, int16_t* d_out, int64_t n_utt, int64_t utt_samples, int64_t utt_stride,
