@@ -66,7 +66,6 @@ void fft_pair_pcm(const uint32_t* w32a, int delta, float* P2, int col) {
   }
 }
 
-inline int slot_of_col(int c) { return (c & ~3) | ((c >> 1) & 1) | ((c & 1) << 1); }
 
 void fft_frame_f32(const float* fr, int frame_len, float* Pcol) {
   FrameThreads th;
@@ -150,7 +149,7 @@ int emul_utterance(const int16_t* pcm, long long n_samples, int feat_mode, float
     for (int w = 0; w < 8; ++w)
       for (int h = 0; h < 2; ++h) {
         const uint32_t* w32 = reinterpret_cast<const uint32_t*>(stage.data()) + (4 * w + h) * (kHop / 2);
-        fft_pair_pcm(w32, kHop, P.data(), 4 * w + 2 * h);
+        fft_pair_pcm(w32, kHop, P.data(), col_of_halfwarp(w, h));
       }
     // mel + log phase: warp g = filter group, lane = P column
     for (int g = 0; g < 8; ++g)

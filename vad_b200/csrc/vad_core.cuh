@@ -423,6 +423,15 @@ VADB_HD void mel2_group_dispatch(int g, const float* P2, float* logE) {
     default: mel2_group<7, PITCH2, OPITCH>(P2, logE); break;
   }
 }
+// Who owns which column of the 32-frame step.  Half-warp h of warp w carries frame slots 4w + h and 4w + h + 2 (PCM of
+// neighbouring slots is 80 words apart, so the two half-warps read different banks) and stores them in adjacent
+// columns c, c + 1 with c = 2 (w & 3) + 8 h + 16 (w >> 2): the second half-warp's columns are 8 further, i.e. 16
+// banks, which makes the 32-lane power stores conflict free.
+VADB_HD int col_of_halfwarp(int w, int h) { return 2 * (w & 3) + 8 * h + 16 * (w >> 2); }
+VADB_HD int slot_of_col(int c) {
+  const int q = c >> 1, w = (q & 3) + 4 * (q >> 3);
+  return 4 * w + ((q >> 2) & 1) + 2 * (c & 1);
+}
 // offset (floats) of power bin `bin` of column `col` in the pair tile
 VADB_HD int p2_index(int bin, int col) { return ((bin >> 1) - kP2FirstRow) * kP2Pitch + 2 * col + (bin & 1); }
 

@@ -136,11 +136,6 @@ struct ShflXchg {
   }
 };
 
-// P-tile column of frame slot fs inside a 32-frame step.  A half-warp carries frame slots
-// 4w + h and 4w + h + 2 (so that the two half-warps' PCM reads fall on different banks) and stores
-// their powers in adjacent columns 4w + 2h, 4w + 2h + 1.
-__host__ __device__ __forceinline__ int slot_of_col(int c) { return (c & ~3) | ((c >> 1) & 1) | ((c & 1) << 1); }
-
 // Four frames of a warp through the FFT: half-warp h = lanes 16h..16h+15, two frames per thread.
 // w32a: first PCM word of frame A; frame B starts `delta` words later.  ex: this half-warp's
 // transpose scratch (kExchFrame 64-bit slots).
@@ -294,7 +289,9 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
   Segment seg;
 
   // (Staggering the block-phase schedule of the two CTAs sharing an SM -- per-SM arrival rank via
-  // %smid -- was tried against the lockstep hypothesis and measured neutral: 232.1 vs 231.1 ms.)
+  // %smid -- was tried against the lockstep hypothesis and measured neutral: 232.1 vs 231.1 ms.  Strict
+  // turn-taking of the FFT phases between the two CTAs through a per-SM word in global memory, so that one
+  // CTA's FFT always overlaps the other's mel / DCT / classifier, was 3.3x SLOWER: 696 vs 212 ms.)
 
   auto issue_load = [&](int step, int buf) {
     const long long start = seg.pcm_start + static_cast<long long>(step) * (kStepFrames * kHop);
@@ -335,7 +332,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
         // read different banks), P columns 4 warp + 2 h, + 1
         f2* ex = reinterpret_cast<f2*>(s_exch) + (warp * 2 + h) * kExchFrame;
         warp_fft_quad<13>(stage32 + (warp * 4 + h) * (kHop / 2), kHop, ex, s_tw1, s_tw2, lane,
-                          P2Store{s_P, warp * 4 + 2 * h});
+                          P2Store{s_P, col_of_halfwarp(warp, h)});
       }
       __syncthreads();
 
@@ -837,7 +834,7 @@ __global__ void __launch_bounds__(kThreads) stream_feed_kernel(const BankParams 
   {
     f2* ex = reinterpret_cast<f2*>(s_exch) + (warp * 2 + h) * kExchFrame;
     const uint32_t* w32 = reinterpret_cast<const uint32_t*>(s_fr + (warp * 4 + h) * kStreamFramePitch);
-    warp_fft_quad<13>(w32, kStreamFramePitch, ex, s_tw1, s_tw2, lane, P2Store{s_P, warp * 4 + 2 * h});
+    warp_fft_quad<13>(w32, kStreamFramePitch, ex, s_tw1, s_tw2, lane, P2Store{s_P, col_of_halfwarp(warp, h)});
   }
   __syncthreads();
   mel2_group_dispatch<kP2Pitch, 32>(warp, s_P + 2 * lane, s_logE + lane);
