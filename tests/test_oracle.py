@@ -194,3 +194,23 @@ def test_ref_io_wav_path_matches_live_process_file_when_mounted(tmp_path):
     want = np.array([np.concatenate(f) for f in feats])
     got = rm.dataset_features(rm.mfcc_utterance(ref_io.file_samples(path)))
     np.testing.assert_allclose(got, want, rtol=0, atol=2e-5)
+
+
+def test_ffn_oracle_cross_checked_against_torch_linear():
+    """The FFN restatement has no reference execution to pin to (Keras 1 is absent), so a second, independent
+    implementation checks it: torch.nn.functional.linear / relu / softmax in float64."""
+    import torch
+    import torch.nn.functional as F
+    w = rm.glorot_ffn(7)
+    w["b1"] = np.linspace(-0.3, 0.3, 64).astype(np.float32)       # non-zero biases too
+    w["b4"] = np.array([0.1, -0.2, 0.05], dtype=np.float32)
+    x = np.random.default_rng(0).standard_normal((257, 39)) * np.array([1.0] * 13 + [3.0] * 13 + [20.0] * 13)
+    h = torch.from_numpy(x)
+    for i in (1, 2, 3):
+        h = F.relu(F.linear(h, torch.from_numpy(w["W%d" % i].astype(np.float64)).T,
+                            torch.from_numpy(w["b%d" % i].astype(np.float64))))
+    logits_t = F.linear(h, torch.from_numpy(w["W4"].astype(np.float64)).T, torch.from_numpy(w["b4"].astype(np.float64)))
+    logits, probs = rm.ffn_forward(x, w)
+    np.testing.assert_allclose(logits, logits_t.numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(probs, F.softmax(logits_t, dim=1).numpy(), rtol=1e-12, atol=1e-14)
+    assert np.array_equal(rm.decide(logits), (logits_t.argmax(dim=1) == 1).numpy().astype(np.uint8))
