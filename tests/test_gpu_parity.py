@@ -409,7 +409,7 @@ def test_process_file_and_scale_features_dropins(env, utts, tmp_path):
     assert out is files
     for ff, w in zip(files, want):
         got = np.array([np.concatenate(f) for f in ff])
-        assert np.all(np.abs(got - w) <= 1e-9 + 1e-9 * np.abs(w))
+        assert np.all(np.abs(got - w) <= 1e-6 + 1e-6 * np.abs(w))   # float32 rows, float64 statistics (vadb200_scale_rows)
 
 
 def test_stm_segments_gather(env, tmp_path):
