@@ -44,11 +44,12 @@ constexpr int kOffExch = kOffPcm + 2 * kStagePad * 2;                       // 2
 constexpr int kOffP = kOffExch + kWarps * 2 * kExchFrame * 8;               // + 34816
 constexpr int kP2Bytes = (kP2Rows * kP2Pitch * 4 + 15) & ~15;               // pair tile: 123 rows x 66 floats
 constexpr int kOffLogE = kOffP + kP2Bytes;                                  // + 32480
-constexpr int kOffRing = kOffLogE + kNMel * 32 * 4;                         // + 3328
+constexpr int kLogEFloats = kNMel * 32;                                     // one step's log-mel tile
+constexpr int kOffRing = kOffLogE + 2 * kLogEFloats * 4;                    // + 6656 (two tiles: the DCT runs one step behind)
 constexpr int kOffTw1 = kOffRing + ((kNCep * kRingPitch * 4 + 15) & ~15);   // + 15040
 constexpr int kOffTw2 = kOffTw1 + 256 * 8;
 constexpr int kOffBar = kOffTw2 + 128 * 8;
-constexpr int kOffSeg = kOffBar + 32;                                       // 4 mbarriers: pcm x2, weights, mma
+constexpr int kOffSeg = kOffBar + 48;                                       // 6 mbarriers: pcm x2, weights, mma, P free, P full
 constexpr int kFusedSmemBytes = kOffSeg + 16;                               // s_seg, s_tmem
 constexpr int kBlockStepsTc = 4;                                            // tensor-core FFN: one M=128 tile
 static_assert(kTcBlobBytes <= kWarps * 2 * kExchFrame * 8 + kP2Bytes, "weight blob must fit exch + P");
@@ -102,6 +103,14 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {  // release.cta
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// One arrival per warp: the __syncwarp orders the other lanes' shared-memory accesses before lane 0's release.
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -140,9 +149,11 @@ struct ShflXchg {
 // w32a: first PCM word of frame A; frame B starts `delta` words later.  ex: this half-warp's
 // transpose scratch (kExchFrame 64-bit slots).
 // store(bin, v): receives |2X|^2 of power bin `bin` for frame A (v.x) and frame B (v.y).
-template <int NZ, class STORE>
+// before_store() runs after the second DFT16 and before the first power value is stored (the fused kernels put the
+// CTA barrier that protects the previous step's power tile there: by then every warp has long left its mel phase).
+template <int NZ, class PRE, class STORE>
 __device__ __forceinline__ void warp_fft_quad(const uint32_t* w32a, int delta, f2* ex, const cf2* s_tw1,
-                                               const cf2* s_tw2, int lane, STORE&& store) {
+                                               const cf2* s_tw2, int lane, PRE&& before_store, STORE&& store) {
   const int t = lane & 15;
   f2 xr[16], xi[16];
   fft_load_pcm2(w32a, delta, t, xr, xi);
@@ -156,6 +167,7 @@ __device__ __forceinline__ void warp_fft_quad(const uint32_t* w32a, int delta, f
   exch_load_plane(ex, t, xi);
   __syncwarp();
   dft16<16>(xr, xi);
+  before_store();
   fft_split_store(xr, xi, t, s_tw2, ShflXchg{lane}, store);
 }
 // The fused kernels' power tile: pair rows (bins 2q, 2q+1 side by side per column, vad_core.cuh p2_index); bins
@@ -273,6 +285,8 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
     mbar_init(&s_bar[1], 1);
     mbar_init(&s_bar[2], 1);
     mbar_init(&s_bar[3], 1);
+    mbar_init(&s_bar[4], kWarps);  // "P free": every warp has finished the mel of the previous step
+    mbar_init(&s_bar[5], kWarps);  // "P full": every warp has stored its power columns of this step
     fence_mbar_init();
   }
   uint32_t tm_base = 0, w_par = 0, mma_par = 0;
@@ -287,6 +301,8 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
 
   unsigned gstep = 0;  // loads issued so far by this CTA == steps started; buffer = gstep & 1
   Segment seg;
+  __syncthreads();                 // mbarrier inits visible
+  warp_arrive(&s_bar[4], lane);    // the power tile starts out free
 
   // (Staggering the block-phase schedule of the two CTAs sharing an SM -- per-SM arrival rank via
   // %smid -- was tried against the lockstep hypothesis and measured neutral: 232.1 vs 231.1 ms.  Strict
@@ -318,6 +334,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
     const int n = seg.n_frames;
     const int nsteps = (n + kStepFrames - 1) / kStepFrames;
     int out_done = (MODE == 0) ? 0 : 2;
+    bool dct_pending = false;  // the previous step's log-mel tile still waits for its DCT
     if (nsteps > 0) issue_load(0, gstep & 1);
     __syncthreads();
 
@@ -326,6 +343,29 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
       if (s + 1 < nsteps) issue_load(s + 1, buf ^ 1);
       mbar_wait(&s_bar[buf], (gstep >> 1) & 1);
 
+      // Two split-phase barriers (mbarrier arrive / wait, one arrival per warp) replace CTA-wide bar.syncs, so a warp
+      // only ever waits for data it needs and the warps of a CTA drift apart instead of marching in lockstep:
+      //   s_bar[4] "P free": arrive after the mel of step s - 1, wait before the first power store of step s
+      //                      (by then the arrivals are ~ one FFT old);
+      //   s_bar[5] "P full": arrive after the last power store, wait before the mel; the DCT of step s - 1 sits
+      //                      between the two, it needs nothing from this step.
+      // Both complete once per step: parity = gstep & 1.
+      const uint32_t par = gstep & 1;
+      auto dct_step = [&](int sd) {
+        if (!(VADB_DBG(p) & 4)) {
+          const float* le = s_logE + (sd & 1) * kLogEFloats + lane;
+          const int col = (sd * kStepFrames + slot_of_col(lane)) % kRing;  // lane = P column
+          if (warp + 8 < kNCep) {
+            float ra, rb;
+            dct_coef2<32>(le, warp, ra, rb);
+            s_ring[warp * kRingPitch + col] = ra;
+            s_ring[(warp + 8) * kRingPitch + col] = rb;
+          } else {
+            s_ring[warp * kRingPitch + col] = dct_coef<32>(le, warp);
+          }
+        }
+      };
+
       // ---- FFT phase ---------------------------------------------------------------------
       const uint32_t* stage32 = reinterpret_cast<const uint32_t*>(s_pcm + buf * kStagePad);
       if (!(VADB_DBG(p) & 1)) {
@@ -333,36 +373,38 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
         // read different banks), P columns 4 warp + 2 h, + 1
         f2* ex = reinterpret_cast<f2*>(s_exch) + (warp * 2 + h) * kExchFrame;
         warp_fft_quad<13>(stage32 + (warp * 4 + h) * (kHop / 2), kHop, ex, s_tw1, s_tw2, lane,
-                          P2Store{s_P, col_of_halfwarp(warp, h)});
+                          [&] { mbar_wait(&s_bar[4], par); }, P2Store{s_P, col_of_halfwarp(warp, h)});
+      } else {
+        mbar_wait(&s_bar[4], par);
       }
-      __syncthreads();
+      warp_arrive(&s_bar[5], lane);
+
+      // ---- DCT -> MFCC ring, one step behind ---------------------------------------------------
+      // The log-mel tile of step s - 1 is complete (every warp arrived on "P free" after its mel).
+      if (dct_pending) dct_step(s - 1);
+      mbar_wait(&s_bar[5], par);
 
       // ---- mel + log phase -----------------------------------------------------------------
       // (a rolled, table-driven mel loop -- one small code body for all warps, weights in shared memory -- was
       // measured 5.8 % slower than these eight straight-line regions: its loads are latency-exposed)
-      if (!(VADB_DBG(p) & 2)) mel2_group_dispatch<kP2Pitch, 32>(warp, s_P + 2 * lane, s_logE + lane);
+      if (!(VADB_DBG(p) & 2))
+        mel2_group_dispatch<kP2Pitch, 32>(warp, s_P + 2 * lane, s_logE + (s & 1) * kLogEFloats + lane);
+      warp_arrive(&s_bar[4], lane);
       const int computed = min((s + 1) * kStepFrames, n);
       const bool block_now = (((s + 1) % kBlk) == 0 || s == nsteps - 1) && !(VADB_DBG(p) & 8);
       const bool tc_now = TC && block_now && (computed - 2 - out_done) > 0;  // block-uniform
-      if (tc_now) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // exch/P generic accesses before the TMA overwrite
-      __syncthreads();
-      if (tc_now && tid == 0 && !(VADB_DBG(p) & 16)) {  // exch + P are idle until the next FFT phase: land the weight blob during the DCT
-        constexpr uint32_t blob_bytes = TC == 2 ? kTc16BlobBytes : kTcBlobBytes;
-        mbar_arrive_expect_tx(&s_bar[2], blob_bytes);
-        bulk_g2s(smem + kOffExch, p.tc_blob, blob_bytes, &s_bar[2]);
-      }
+      dct_pending = !block_now;
 
-      // ---- DCT phase -> MFCC ring -----------------------------------------------------------
-      if (!(VADB_DBG(p) & 4)) {
-        const int col = (s * kStepFrames + slot_of_col(lane)) % kRing;  // lane = P column
-        if (warp + 8 < kNCep) {
-          float ra, rb;
-          dct_coef2<32>(s_logE + lane, warp, ra, rb);
-          s_ring[warp * kRingPitch + col] = ra;
-          s_ring[(warp + 8) * kRingPitch + col] = rb;
-        } else {
-          s_ring[warp * kRingPitch + col] = dct_coef<32>(s_logE + lane, warp);
+      // A step that is followed by a block phase transforms its own log-mel tile right away, behind a CTA barrier.
+      if (block_now) {
+        if (tc_now) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // exch/P generic accesses before the TMA overwrite
+        __syncthreads();
+        if (tc_now && tid == 0 && !(VADB_DBG(p) & 16)) {  // exch + P are idle until the next FFT phase: land the weight blob during the DCT
+          constexpr uint32_t blob_bytes = TC == 2 ? kTc16BlobBytes : kTcBlobBytes;
+          mbar_arrive_expect_tx(&s_bar[2], blob_bytes);
+          bulk_g2s(smem + kOffExch, p.tc_blob, blob_bytes, &s_bar[2]);
         }
+        dct_step(s);
       }
 
       if (block_now) {
@@ -835,7 +877,7 @@ __global__ void __launch_bounds__(kThreads) stream_feed_kernel(const BankParams 
   {
     f2* ex = reinterpret_cast<f2*>(s_exch) + (warp * 2 + h) * kExchFrame;
     const uint32_t* w32 = reinterpret_cast<const uint32_t*>(s_fr + (warp * 4 + h) * kStreamFramePitch);
-    warp_fft_quad<13>(w32, kStreamFramePitch, ex, s_tw1, s_tw2, lane, P2Store{s_P, col_of_halfwarp(warp, h)});
+    warp_fft_quad<13>(w32, kStreamFramePitch, ex, s_tw1, s_tw2, lane, [] {}, P2Store{s_P, col_of_halfwarp(warp, h)});
   }
   __syncthreads();
   mel2_group_dispatch<kP2Pitch, 32>(warp, s_P + 2 * lane, s_logE + lane);
