@@ -155,18 +155,14 @@ int emul_utterance(const int16_t* pcm, long long n_samples, int feat_mode, float
     for (int g = 0; g < 8; ++g)
       for (int lane = 0; lane < 32; ++lane)
         mel2_group_dispatch<kP2Pitch, 32>(g, P.data() + 2 * lane, logE.data() + lane);
-    // DCT phase: warp w -> coefficients w and w + 8
-    for (int w = 0; w < 8; ++w)
+    // DCT phase: warp w -> coefficients 2w and 2w + 1 (warp 7 idles)
+    for (int w = 0; w < 7; ++w)
       for (int lane = 0; lane < 32; ++lane) {
         const int f = s * kStepFrames + slot_of_col(lane);
-        if (w + 8 < kNCep) {
-          float ra, rb;
-          dct_coef2<32>(logE.data() + lane, w, ra, rb);
-          ring[w * kRing + f % kRing] = ra;
-          ring[(w + 8) * kRing + f % kRing] = rb;
-        } else {
-          ring[w * kRing + f % kRing] = dct_coef<32>(logE.data() + lane, w);
-        }
+        float ra, rb;
+        dct_coef2<32>(logE.data() + lane, w, ra, rb);
+        ring[2 * w * kRing + f % kRing] = ra;
+        if (2 * w + 1 < kNCep) ring[(2 * w + 1) * kRing + f % kRing] = rb;
       }
     const int computed = std::min((s + 1) * kStepFrames, n);
     if (mfcc_out)

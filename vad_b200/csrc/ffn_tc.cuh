@@ -39,12 +39,14 @@
 namespace vadb {
 
 constexpr int kTcK1 = 48, kTcN1 = 64;   // 39 -> 48: two 24-column halves (coefficients 0-6 | 7-12), see tc_feat_col
-// Layer-1 K order: feature (g, k) (g = 0 z, 1 d1, 2 d2; reference order g*13 + k) sits in column
-// 3k + g for k < 7 and 24 + 3(k-7) + g for k >= 7, so that the two threads sharing a frame can each
-// build the features of one coefficient range and store one contiguous 24-column block.
+// Layer-1 K order: feature (g, k) (g = 0 z, 1 d1, 2 d2; reference order g*13 + k) of coefficient pair q = k / 2,
+// element e = k % 2 sits in column 6 q + 2 g + e for q < 4 and 24 + 6 (q - 4) + 2 g + e for q >= 4, so that the two
+// threads sharing a frame each build the features of one range of coefficient pairs with packed arithmetic
+// (vad_core.cuh window_features_pairs) and store one contiguous 24-column block whose fp16 column pairs are the
+// packed results themselves.  Columns 40, 41 (the missing coefficient 13) and 42..47 are zero.
 __host__ __device__ constexpr int tc_feat_col(int feat) {
-  const int g = feat / 13, k = feat % 13;
-  return k < 7 ? 3 * k + g : 24 + 3 * (k - 7) + g;
+  const int g = feat / 13, k = feat % 13, q = k / 2, e = k % 2;
+  return q < 4 ? 6 * q + 2 * g + e : 24 + 6 * (q - 4) + 2 * g + e;
 }
 constexpr int kTcK2 = 64, kTcN2 = 32;
 constexpr int kTcK3 = 32, kTcN3 = 16;
@@ -170,6 +172,7 @@ inline bool tc16_pack_weights(const FfnParams& p, unsigned char* blob /*kTc16Blo
     const int ew = wmax > 0.0 ? static_cast<int>(std::floor(std::log2(16000.0 / wmax))) : 0;
     if (ea > 60 || ew > 60 || ew < -60) return false;
     const float sa = std::ldexp(1.0f, -ea), sw = std::ldexp(1.0f, ew);
+    if (l == 0 && ea != 0) return false;  // the feature bounds keep layer 1's activations unscaled (pre[0] == 1)
     fb.pre[l] = sa;
     fb.post[l] = std::ldexp(1.0f, ea - ew);
     tc16_pack_layer(W[l], kin[l], nout[l], Kp[l], Np[l], sw, reinterpret_cast<uint16_t*>(blob + off[l]), l == 0);
@@ -181,6 +184,11 @@ inline bool tc16_pack_weights(const FfnParams& p, unsigned char* blob /*kTc16Blo
     }
     bound = nb;
   }
+  for (int l = 0; l < 3; ++l) fb.postp[l] = fb.post[l] * fb.pre[l + 1];
+  fb.postp[3] = fb.post[3];
+  for (int j = 0; j < kH1; ++j) fb.c1[j] = p.b1[j] * fb.pre[1];
+  for (int j = 0; j < kH2; ++j) fb.c2[j] = p.b2[j] * fb.pre[2];
+  for (int j = 0; j < kH3; ++j) fb.c3[j] = p.b3[j] * fb.pre[3];
   return true;
 }
 
@@ -458,19 +466,22 @@ __device__ __forceinline__ void tc16_issue_layer(uint32_t tm_base, uint32_t d_co
   }
   umma_commit(done_bar);
 }
-// (x0, x1) -> one 32-bit word of hi parts and one of lo parts (element 0 in the low half)
-__device__ __forceinline__ void tc16_split2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(x0, x1);
+// (x0, x1) -> one 32-bit word of hi parts and one of lo parts (element 0 in the low half); the residual is one FADD2
+__device__ __forceinline__ void tc16_split2(f2 x, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(x.x, x.y);
   const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+  const f2 r = vsub(x, mk2(hf.x, hf.y));
+  const __half2 l = __floats2half2_rn(r.x, r.y);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
-// Epilogue of a hidden layer: D (NOUT fp32 columns at d_col, second half NOUT further) -> x post-scale, + bias,
-// ReLU, x pre-scale of the next layer, fp16 hi/lo split -> A operand of the next layer.
+// Epilogue of a hidden layer: D (NOUT fp32 columns at d_col, second half NOUT further) -> x (post-scale x next layer's
+// pre-scale), + scaled bias, ReLU, fp16 hi/lo split -> A operand of the next layer.  Column pairs are processed with
+// packed fp32 arithmetic (tcgen05.ld delivers neighbouring columns in neighbouring registers).
+// cbias: bias x next pre-scale (FfnBias::c1..c3), postp: FfnBias::postp[l].
 template <int NOUT, int HALVES>
-__device__ __forceinline__ void tc16_hidden_epilogue(uint32_t tl, uint32_t d_col, const float* bias, float post,
-                                                     float pre_next, int hidx) {
+__device__ __forceinline__ void tc16_hidden_epilogue(uint32_t tl, uint32_t d_col, const float* cbias, float postp,
+                                                     int hidx) {
   constexpr int W = NOUT / HALVES;         // fp32 columns per thread: 64, 32, 16 or 8
   constexpr int CH = W >= 16 ? 16 : 8;
   const int base = hidx * W;
@@ -487,10 +498,12 @@ __device__ __forceinline__ void tc16_hidden_epilogue(uint32_t tl, uint32_t d_col
     tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < CH; i += 2) {
-      const float a0 = fmaxf(fmaf(__uint_as_float(v[i]) + __uint_as_float(u[i]), post, bias[base + c0 + i]), 0.0f);
-      const float a1 =
-          fmaxf(fmaf(__uint_as_float(v[i + 1]) + __uint_as_float(u[i + 1]), post, bias[base + c0 + i + 1]), 0.0f);
-      tc16_split2(a0 * pre_next, a1 * pre_next, hi[i / 2], lo[i / 2]);
+      const f2 d = vadd(mk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
+                        mk2(__uint_as_float(u[i]), __uint_as_float(u[i + 1])));
+      f2 a = vfma(d, mk2(postp, postp), mk2(cbias[base + c0 + i], cbias[base + c0 + i + 1]));
+      a.x = fmaxf(a.x, 0.0f);
+      a.y = fmaxf(a.y, 0.0f);
+      tc16_split2(a, hi[i / 2], lo[i / 2]);
     }
     if constexpr (CH == 16) {
       tmem_st8(tl + kTmA + (base + c0) / 2, hi);
@@ -502,13 +515,14 @@ __device__ __forceinline__ void tc16_hidden_epilogue(uint32_t tl, uint32_t d_col
   }
   tmem_wait_st();
 }
-// 24 layer-1 A columns of one half (features of coefficients 0-6 / 7-12) -> 12 + 12 packed columns.
-__device__ __forceinline__ void tc16_store_a1_half(uint32_t tl, int hidx, const float (&xl)[24], float pre) {
+// 24 layer-1 A columns of one half (features of coefficient pairs 0-3 / 4-6, unscaled: FfnBias::pre[0] == 1)
+// -> 12 + 12 packed columns.
+__device__ __forceinline__ void tc16_store_a1_half(uint32_t tl, int hidx, const float (&xl)[24]) {
   uint32_t hi[8], lo[8], hi4[4], lo4[4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) tc16_split2(xl[2 * i] * pre, xl[2 * i + 1] * pre, hi[i], lo[i]);
+  for (int i = 0; i < 8; ++i) tc16_split2(mk2(xl[2 * i], xl[2 * i + 1]), hi[i], lo[i]);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) tc16_split2(xl[16 + 2 * i] * pre, xl[17 + 2 * i] * pre, hi4[i], lo4[i]);
+  for (int i = 0; i < 4; ++i) tc16_split2(mk2(xl[16 + 2 * i], xl[17 + 2 * i]), hi4[i], lo4[i]);
   const uint32_t b = tl + kTmA + 12 * hidx;
   tmem_st8(b, hi);
   tmem_st4(b + 8, hi4);
@@ -530,7 +544,7 @@ __device__ __forceinline__ uint32_t ffn_tc16_tile(const FfnBias& fb, float (&log
   }
   tc_mbar_wait(mma_bar, par); par ^= 1u;
   tc_fence_after();
-  tc16_hidden_epilogue<kTcN1, HALVES>(tl, kTmD1, fb.b1, fb.post[0], fb.pre[1], hidx);
+  tc16_hidden_epilogue<kTcN1, HALVES>(tl, kTmD1, fb.c1, fb.postp[0], hidx);
   tc_fence_before();
   tc_bar<HALVES>();
   if (is_issuer) {
@@ -539,7 +553,7 @@ __device__ __forceinline__ uint32_t ffn_tc16_tile(const FfnBias& fb, float (&log
   }
   tc_mbar_wait(mma_bar, par); par ^= 1u;
   tc_fence_after();
-  tc16_hidden_epilogue<kTcN2, HALVES>(tl, kTmD2, fb.b2, fb.post[1], fb.pre[2], hidx);
+  tc16_hidden_epilogue<kTcN2, HALVES>(tl, kTmD2, fb.c2, fb.postp[1], hidx);
   tc_fence_before();
   tc_bar<HALVES>();
   if (is_issuer) {
@@ -548,7 +562,7 @@ __device__ __forceinline__ uint32_t ffn_tc16_tile(const FfnBias& fb, float (&log
   }
   tc_mbar_wait(mma_bar, par); par ^= 1u;
   tc_fence_after();
-  tc16_hidden_epilogue<kTcN3, HALVES>(tl, kTmD3, fb.b3, fb.post[2], fb.pre[3], hidx);
+  tc16_hidden_epilogue<kTcN3, HALVES>(tl, kTmD3, fb.c3, fb.postp[2], hidx);
   tc_fence_before();
   tc_bar<HALVES>();
   if (is_issuer) {

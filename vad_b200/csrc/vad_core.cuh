@@ -70,7 +70,7 @@ constexpr int kMelPairs = mel_qoff(kNMel);
 
 struct alignas(16) MelDctTables {
   float melw2[2 * kMelPairs + 2];  // pair weights x 2^-20, filter-major (mel_qoff); first: 16-byte aligned for LDCU.128
-  float dctp[5][kNMel][2];         // (M[p][n], M[p + 8][n]) for the two coefficients a warp owns, p = 0 .. 4
+  float dctp[7][kNMel][2];         // (M[2p][n], M[2p + 1][n]) for the coefficient pair a warp owns, p = 0 .. 6 (M[13] = 0)
   float melw[448];                 // 444 non-zero triangle weights x 2^-20, filter-major (kMelOff)
   float dct[kNCep * kNMel];        // M = lifter[k] * dct2_ortho[k][n] * log10(2)   (input is log2 E)
 };
@@ -90,10 +90,14 @@ struct FfnParams {
   float b4[kNCls];
   float pad_[1];
 };
-struct FfnBias {                 // what the tensor-core FFN needs besides its weight blob
+struct alignas(8) FfnBias {      // what the tensor-core FFN needs besides its weight blob
   float b1[kH1], b2[kH2], b3[kH3], b4[kNCls], pad_[1];
-  float pre[4];                  // fp16 operand path: power-of-two scale of layer l's input activations
+  float pre[4];                  // fp16 operand path: power-of-two scale of layer l's input activations (pre[0] == 1)
   float post[4];                 // ... and the exact inverse of (weight scale x activation scale)
+  // fp16 path, hidden layers: the next layer's activation scale folded into this layer's epilogue (powers of two,
+  // so relu(d post + b) pre' == relu(d (post pre') + b pre') bit for bit): c_l = b_l pre[l+1], postp[l] = post[l] pre[l+1]
+  float c1[kH1], c2[kH2], c3[kH3];
+  float postp[4];
 };
 struct FfnNone { int unused; };
 
@@ -451,8 +455,9 @@ VADB_HD float dct_coef(const float* logE, int c) {
   return (a0 + a2) + (a1 + a3);
 }
 
-// Coefficients p and p + 8 of the same frame at once (p = 0 .. 4): one FFMA2 per log-energy on the coefficient
-// pair, the log-energy broadcast to both halves.  Per coefficient the chains are those of dct_coef (bit-identical).
+// Coefficients 2p and 2p + 1 of the same frame at once (p = 0 .. 6; coefficient 13 is a zero row): one FFMA2 per
+// log-energy on the coefficient pair, the log-energy broadcast to both halves.  Per coefficient the chains are those
+// of dct_coef (bit-identical).  The pair is what one 64-bit slot of the fused kernels' MFCC ring holds.
 template <int PITCH>
 VADB_HD void dct_coef2(const float* logE, int p, float& ra, float& rb) {
   f2 a0 = mk2(0.0f, 0.0f), a1 = a0, a2 = a0, a3 = a0;
@@ -505,33 +510,63 @@ VADB_HD bool window_features(const float (&r)[5][kNCep], int mode, float (&x)[kN
   return ok;
 }
 
-// Features of the coefficient range [K0, K1) only, ordered (k, g): out[3 (k-K0) + g] with g = 0 z,
-// 1 d1, 2 d2 -- the layer-1 column order of the tensor-core FFN (ffn_tc.cuh: tc_feat_col).
-// ring: MFCC ring [coef][PITCH], RING slots used; centre frame c.  Same arithmetic as window_features.
-template <int K0, int K1, int RING, int PITCH, int NOUT>
-VADB_HD bool window_features_range(const float* ring, int c, int mode, float (&out)[NOUT]) {
+// ---- MFCC ring of the fused kernels: coefficient pairs side by side --------------------------------------------------
+// Row q holds coefficients 2q, 2q+1 of every slot as one 64-bit element, so the window features of a coefficient pair
+// are built with packed (FADD2 / FFMA2 / FMUL2) arithmetic from five LDS.64.  Element 1 of row 6 is never written.
+constexpr int kRingRows = (kNCep + 1) / 2;  // 7
+VADB_HD constexpr int ring_pitch(int ring) { return 2 * ring + 2; }   // floats per row
+VADB_HD constexpr int ring_idx(int k, int slot, int ring) { return (k >> 1) * ring_pitch(ring) + 2 * slot + (k & 1); }
+
+VADB_HD uint32_t fbits(float x) {
+#if defined(__CUDA_ARCH__)
+  return __float_as_uint(x);
+#else
+  uint32_t u;
+  __builtin_memcpy(&u, &x, 4);
+  return u;
+#endif
+}
+// Window features of the coefficient pairs [Q0, Q1), centre frame c, in the layer-1 column order of the
+// tensor-core FFN (ffn_tc.cuh tc_feat_col): out[6 j + 2 g + e] = feature g (0 z, 1 d1, 2 d2) of coefficient
+// 2 (Q0 + j) + e.  Per coefficient the arithmetic is that of window_features (packed ops round like scalar ones);
+// "all five equal" is tested on the bit patterns (+-0 mixes and NaNs end in NaN either way: var = 0 -> 0 x inf).
+template <int Q0, int Q1, int RING, int NOUT>
+VADB_HD bool window_features_pairs(const float* ring2, int c, int mode, float (&out)[NOUT]) {
+  static_assert(6 * (Q1 - Q0) <= NOUT, "output too small");
+  constexpr int PITCH = ring_pitch(RING);
   bool ok = true;
-  static_assert(3 * (K1 - K0) <= NOUT, "output too small");
-  const int c0i = (c - 2) % RING, c1i = (c - 1) % RING, c2i = c % RING, c3i = (c + 1) % RING, c4i = (c + 2) % RING;
+  const int i0 = 2 * ((c - 2) % RING), i1 = 2 * ((c - 1) % RING), i2 = 2 * (c % RING), i3 = 2 * ((c + 1) % RING),
+            i4 = 2 * ((c + 2) % RING);
 #pragma unroll
-  for (int k = K0; k < K1; ++k) {
-    const float* row = ring + k * PITCH;
-    const float c0 = row[c0i], c1 = row[c1i], c2 = row[c2i], c3 = row[c3i], c4 = row[c4i];
-    float z = c2;
+  for (int q = Q0; q < Q1; ++q) {
+    const float* row = ring2 + q * PITCH;
+    f2 c0 = mk2(row[i0], row[i0 + 1]), c1 = mk2(row[i1], row[i1 + 1]), c2 = mk2(row[i2], row[i2 + 1]),
+       c3 = mk2(row[i3], row[i3 + 1]), c4 = mk2(row[i4], row[i4 + 1]);
+    const bool pad = 2 * q + 1 >= kNCep;  // compile-time after unrolling: element 1 is not a coefficient
+    if (pad) { c0.y = 0.0f; c1.y = 1.0f; c2.y = 2.0f; c3.y = 3.0f; c4.y = 4.0f; }
+    f2 z = c2;
     if (mode == 0) {
-      const float mu = ((((c0 + c1) + c2) + c3) + c4) * 0.2f;
-      const float d0 = c0 - mu, d1 = c1 - mu, d2 = c2 - mu, d3 = c3 - mu, d4 = c4 - mu;
-      const float var = fmaf(d4, d4, fmaf(d3, d3, fmaf(d2, d2, fmaf(d1, d1, d0 * d0)))) * 0.2f;
-      const bool alleq = (c0 == c1) && (c1 == c2) && (c2 == c3) && (c3 == c4);
-      z = alleq ? NAN : d2 * vadb_rsqrt(var);
-      ok = ok && (fabsf(z) <= 3.0e38f);
+      const f2 mu = vmuls(0.2f, vadd(vadd(vadd(vadd(c0, c1), c2), c3), c4));
+      const f2 d0 = vsub(c0, mu), d1 = vsub(c1, mu), d2 = vsub(c2, mu), d3 = vsub(c3, mu), d4 = vsub(c4, mu);
+      const f2 var = vmuls(0.2f, vfma(d4, d4, vfma(d3, d3, vfma(d2, d2, vfma(d1, d1, vmul(d0, d0))))));
+      const bool eqx = ((fbits(c0.x) ^ fbits(c1.x)) | (fbits(c1.x) ^ fbits(c2.x)) | (fbits(c2.x) ^ fbits(c3.x)) |
+                        (fbits(c3.x) ^ fbits(c4.x))) == 0u;
+      const bool eqy = ((fbits(c0.y) ^ fbits(c1.y)) | (fbits(c1.y) ^ fbits(c2.y)) | (fbits(c2.y) ^ fbits(c3.y)) |
+                        (fbits(c3.y) ^ fbits(c4.y))) == 0u;
+      z = vmul(d2, mk2(vadb_rsqrt(var.x), vadb_rsqrt(var.y)));
+      if (eqx) z.x = NAN;
+      if (eqy) z.y = NAN;
+      ok = ok && (fabsf(z.x) <= 3.0e38f) && (fabsf(z.y) <= 3.0e38f);
     }
-    out[3 * (k - K0) + 0] = z;
-    out[3 * (k - K0) + 1] = c3 - c1;
-    out[3 * (k - K0) + 2] = (c4 - z) - (z - c0);
+    const f2 e1 = vsub(c3, c1);
+    const f2 e2 = vsub(vsub(c4, z), vsub(z, c0));
+    float* o = out + 6 * (q - Q0);
+    o[0] = z.x;  o[1] = pad ? 0.0f : z.y;
+    o[2] = e1.x; o[3] = pad ? 0.0f : e1.y;
+    o[4] = e2.x; o[5] = pad ? 0.0f : e2.y;
   }
 #pragma unroll
-  for (int i = 3 * (K1 - K0); i < NOUT; ++i) out[i] = 0.0f;
+  for (int i = 6 * (Q1 - Q0); i < NOUT; ++i) out[i] = 0.0f;
   return ok;
 }
 

@@ -90,12 +90,12 @@ inline void pack_mel_pairs(const double* fb /*[26][256]*/, float* melw2) {
       }
   melw2[2 * kMelPairs] = melw2[2 * kMelPairs + 1] = 0.0f;
 }
-// (M[p][n], M[p + 8][n]) pairs for dct_coef2
+// (M[2p][n], M[2p + 1][n]) pairs for dct_coef2 (row 13 does not exist: zeros)
 inline void pack_dct_pairs(const float* dct /*[13][26]*/, float (*dctp)[kNMel][2]) {
-  for (int p = 0; p < 5; ++p)
+  for (int p = 0; p < 7; ++p)
     for (int n = 0; n < kNMel; ++n) {
-      dctp[p][n][0] = dct[p * kNMel + n];
-      dctp[p][n][1] = dct[(p + 8) * kNMel + n];
+      dctp[p][n][0] = dct[2 * p * kNMel + n];
+      dctp[p][n][1] = 2 * p + 1 < kNCep ? dct[(2 * p + 1) * kNMel + n] : 0.0f;
     }
 }
 

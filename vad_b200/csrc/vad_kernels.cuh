@@ -33,7 +33,6 @@ constexpr int kThreads = 256;
 constexpr int kWarps = 8;
 constexpr int kStepFrames = 32;
 constexpr int kRing = 288;                                     // MFCC ring slots (modulus)
-constexpr int kRingPitch = kRing + 1;                          // odd row pitch: coefficient-strided reads spread over banks
 constexpr int kPPitch = 34;                                    // == 2 (mod 32): conflict-free P stores
 constexpr int kStageSamples = (kStepFrames - 1) * kHop + kFrame;  // 5360
 constexpr int kStagePad = 5376;                                // samples; 10752 B, 128-B multiple
@@ -46,7 +45,7 @@ constexpr int kP2Bytes = (kP2Rows * kP2Pitch * 4 + 15) & ~15;               // p
 constexpr int kOffLogE = kOffP + kP2Bytes;                                  // + 32480
 constexpr int kLogEFloats = kNMel * 32;                                     // one step's log-mel tile
 constexpr int kOffRing = kOffLogE + 2 * kLogEFloats * 4;                    // + 6656 (two tiles: the DCT runs one step behind)
-constexpr int kOffTw1 = kOffRing + ((kNCep * kRingPitch * 4 + 15) & ~15);   // + 15040
+constexpr int kOffTw1 = kOffRing + ((kRingRows * ring_pitch(kRing) * 4 + 15) & ~15);  // + 16192: coefficient-pair rows
 constexpr int kOffTw2 = kOffTw1 + 256 * 8;
 constexpr int kOffBar = kOffTw2 + 128 * 8;
 constexpr int kOffSeg = kOffBar + 48;                                       // 6 mbarriers: pcm x2, weights, mma, P free, P full
@@ -355,13 +354,12 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
         if (!(VADB_DBG(p) & 4)) {
           const float* le = s_logE + (sd & 1) * kLogEFloats + lane;
           const int col = (sd * kStepFrames + slot_of_col(lane)) % kRing;  // lane = P column
-          if (warp + 8 < kNCep) {
+          if (warp < kRingRows) {  // warp w: coefficients 2w, 2w + 1 -> one 64-bit ring element (warp 7 idles)
             float ra, rb;
             dct_coef2<32>(le, warp, ra, rb);
-            s_ring[warp * kRingPitch + col] = ra;
-            s_ring[(warp + 8) * kRingPitch + col] = rb;
-          } else {
-            s_ring[warp * kRingPitch + col] = dct_coef<32>(le, warp);
+            float* dst = s_ring + ring_idx(2 * warp, col, kRing);
+            if (2 * warp + 1 < kNCep) *reinterpret_cast<float2*>(dst) = make_float2(ra, rb);
+            else dst[0] = ra;
           }
         }
       };
@@ -417,7 +415,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
             int fr = j / kNCep, cf = j - fr * kNCep;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              if (i < cnt) v[i] = s_ring[cf * kRingPitch + (first + fr) % kRing];
+              if (i < cnt) v[i] = s_ring[ring_idx(cf, (first + fr) % kRing, kRing)];
               if (++cf == kNCep) { cf = 0; ++fr; }
             }
           });
@@ -433,11 +431,11 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
             for (int i = 0; i < 4; ++i) {
               if (i < cnt) {
                 const int c = first + rr;
-                const float* row = s_ring + cf * kRingPitch;
-                const float c2 = row[c % kRing];
+                const float* row = s_ring + ring_idx(cf, 0, kRing);  // element stride 2
+                const float c2 = row[2 * (c % kRing)];
                 v[i] = grp == 0 ? c2
-                     : grp == 1 ? row[(c + 1) % kRing] - row[(c - 1) % kRing]
-                                : (row[(c + 2) % kRing] - c2) - (c2 - row[(c - 2) % kRing]);
+                     : grp == 1 ? row[2 * ((c + 1) % kRing)] - row[2 * ((c - 1) % kRing)]
+                                : (row[2 * ((c + 2) % kRing)] - c2) - (c2 - row[2 * ((c - 2) % kRing)]);
               }
               if (++cf == kNCep) { cf = 0; if (++grp == 3) { grp = 0; ++rr; } }
             }
@@ -451,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
             for (int d = 0; d < 5; ++d) {
               const int col = (c - 2 + d) % kRing;
 #pragma unroll
-              for (int k = 0; k < kNCep; ++k) r[d][k] = s_ring[k * kRingPitch + col];
+              for (int k = 0; k < kNCep; ++k) r[d][k] = s_ring[ring_idx(k, col, kRing)];
             }
             if constexpr (MODE == 2 && TC == 0)
               classify_row(ffn, r, p.feat_mode, p.labels, p.logits, p.feats, seg.out_start - p.row_base + (c - 2));
@@ -482,19 +480,21 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 24; ++i) xl[i] = 0.5f;
               } else {
-                ok_half = (hidx == 0) ? window_features_range<0, 7, kRing, kRingPitch, 24>(s_ring, c, p.feat_mode, xl)
-                                      : window_features_range<7, 13, kRing, kRingPitch, 24>(s_ring, c, p.feat_mode, xl);
+                ok_half = (hidx == 0) ? window_features_pairs<0, 4, kRing, 24>(s_ring, c, p.feat_mode, xl)
+                                      : window_features_pairs<4, 7, kRing, 24>(s_ring, c, p.feat_mode, xl);
               }
               s_logE[tid] = ok_half ? 1.0f : 0.0f;
               if (ts) ts[1] = clock64();
-              if constexpr (TC == 2) tc16_store_a1_half(tl, hidx, xl, ffn.pre[0]);
+              if constexpr (TC == 2) tc16_store_a1_half(tl, hidx, xl);
               else tc_store_a1_half(tl, hidx, xl);
               if (p.feats && valid) {
                 const long long row = seg.out_start - p.row_base + (c - 2);
-                const int k0 = hidx ? 7 : 0, nk = hidx ? 6 : 7;
-                for (int k = 0; k < nk; ++k)
+                const int k0 = hidx ? 8 : 0, nk = hidx ? 5 : 8;  // xl[6 (k / 2) + 2 g + k % 2], k relative to k0
 #pragma unroll
-                  for (int g = 0; g < 3; ++g) p.feats[row * kNFeat + g * kNCep + k0 + k] = xl[3 * k + g];
+                for (int k = 0; k < 8; ++k)
+#pragma unroll
+                  for (int g = 0; g < 3; ++g)
+                    if (k < nk) p.feats[row * kNFeat + g * kNCep + k0 + k] = xl[6 * (k >> 1) + 2 * g + (k & 1)];
               }
               if (!(VADB_DBG(p) & 16)) mbar_wait(&s_bar[2], w_par);  // weight blob landed (issued before the DCT phase)
               if (ts) ts[2] = clock64();
@@ -593,8 +593,8 @@ __global__ void __launch_bounds__(128) ffn_tc_rows_kernel(const float* x, long l
       else h1[col - 24] = v[f];
     }
     if constexpr (KIND == 2) {
-      tc16_store_a1_half(tl, 0, h0, fb.pre[0]);
-      tc16_store_a1_half(tl, 1, h1, fb.pre[0]);
+      tc16_store_a1_half(tl, 0, h0);
+      tc16_store_a1_half(tl, 1, h1);
     } else {
       tc_store_a1_half(tl, 0, h0);
       tc_store_a1_half(tl, 1, h1);
