@@ -137,7 +137,7 @@ int emul_utterance(const int16_t* pcm, long long n_samples, int feat_mode, float
   // the ring); the emulation computes all T so the MFCC rows can be checked too.
   const int n = static_cast<int>(T);
   const int nsteps = (n + kStepFrames - 1) / kStepFrames;
-  std::vector<float> P(kP2Rows * kP2Pitch), logE(kNMel * 32), ring(kNCep * kRing);
+  std::vector<float> P(kP2RowsAlloc * kP2Pitch), logE(kNMel * 32), ring(kNCep * kRing);
   std::vector<int16_t> stage(kStageSamples + 8);
   int out_done = 2;
   for (int s = 0; s < nsteps; ++s) {

@@ -59,6 +59,8 @@ constexpr int kH1 = 64, kH2 = 32, kH3 = 16, kNCls = 3;  // ffn_trainer.py:108-11
 constexpr int kP2Pitch = 66;                       // floats per pair row: 32 columns x 2 bins, + 2 (== 2 mod 32)
 constexpr int kP2FirstRow = kMelFirstBin / 2;      // bins below 10 carry no mel weight
 constexpr int kP2Rows = kBins / 2 - kP2FirstRow;   // 123
+constexpr int kP2RowsAlloc = kP2Rows + 1;          // + the row "bin 256" lands in: a write-only sink that makes every
+                                                   // power store unconditional (bins below the first mel bin go there too)
 constexpr int mel_q0(int m) { return kMelLo[m] >> 1; }
 constexpr int mel_nq(int m) { return ((kMelHi[m] - 1) >> 1) - (kMelLo[m] >> 1) + 1; }
 constexpr int mel_qoff(int m) {
@@ -313,9 +315,15 @@ VADB_HD void split_pair(V ar, V ai, V br, V bi, float wr, float wi, V& plo, V& p
 #if defined(__CUDACC__)
 #pragma nv_exec_check_disable
 #endif
+// STORE::kHasSink: the store redirects bins it does not keep (and bin 256) to a sink row, so every store below is
+// unconditional -- no divergent branches around the first pair, the (0, 256) pair and thread 0's bin 128.
+template <class S, class = void> struct store_has_sink { static constexpr bool value = false; };
+template <class S> struct store_has_sink<S, std::enable_if_t<S::kHasSink>> { static constexpr bool value = true; };
+
 template <class V, class TW2, class XCH, class STORE>
 VADB_HD void fft_split_store_tw(const V (&xr)[16], const V (&xi)[16], int k1, TW2&& tw2,
                                 XCH&& xch, STORE&& store) {
+  constexpr bool kSink = store_has_sink<std::remove_cv_t<std::remove_reference_t<STORE>>>::value;
   V sr[16], si[16];
   static_for<8, 16>([&](auto J) {
     constexpr int j = J;
@@ -332,9 +340,13 @@ VADB_HD void fft_split_store_tw(const V (&xr)[16], const V (&xi)[16], int k1, TW
     split_pair(xr[k2], xi[k2], br, bi, w.x, w.y, plo, phi);
     const int lo = k1 + 16 * k2;
     store(lo, plo);
-    if (k2 != 0 || k1 != 0) store(256 - lo, phi);
+    if (kSink || k2 != 0 || k1 != 0) store(256 - lo, phi);   // thread 0's (0, 256) pair: bin 256 is the sink
   });
-  if (k1 == 0) store(128, vmuls(4.0f, vfma(xr[8], xr[8], vmul(xi[8], xi[8]))));
+  if constexpr (kSink) {
+    store(k1 == 0 ? 128 : 256, vmuls(4.0f, vfma(xr[8], xr[8], vmul(xi[8], xi[8]))));
+  } else {
+    if (k1 == 0) store(128, vmuls(4.0f, vfma(xr[8], xr[8], vmul(xi[8], xi[8]))));
+  }
 }
 #if defined(__CUDACC__)
 #pragma nv_exec_check_disable

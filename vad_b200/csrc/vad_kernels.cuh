@@ -41,7 +41,7 @@ constexpr int kBlockSteps = 8;                                 // block phase ev
 constexpr int kOffPcm = 0;
 constexpr int kOffExch = kOffPcm + 2 * kStagePad * 2;                       // 21504
 constexpr int kOffP = kOffExch + kWarps * 2 * kExchFrame * 8;               // + 34816
-constexpr int kP2Bytes = (kP2Rows * kP2Pitch * 4 + 15) & ~15;               // pair tile: 123 rows x 66 floats
+constexpr int kP2Bytes = (kP2RowsAlloc * kP2Pitch * 4 + 15) & ~15;          // pair tile: 123 rows x 66 floats + sink row
 constexpr int kOffLogE = kOffP + kP2Bytes;                                  // + 32480
 constexpr int kLogEFloats = kNMel * 32;                                     // one step's log-mel tile
 constexpr int kOffRing = kOffLogE + 2 * kLogEFloats * 4;                    // + 6656 (two tiles: the DCT runs one step behind)
@@ -172,14 +172,13 @@ __device__ __forceinline__ void warp_fft_quad(const uint32_t* w32a, int delta, f
 // The fused kernels' power tile: pair rows (bins 2q, 2q+1 side by side per column, vad_core.cuh p2_index); bins
 // below the first mel bin are dropped.  Columns col (frame A) and col + 1 (frame B).
 struct P2Store {
+  static constexpr bool kHasSink = true;  // row kP2Rows ("bin 256") swallows what the mel never reads
   float* P2;
   int col;
   __device__ __forceinline__ void operator()(int bin, f2 v) const {
-    if (bin >= kMelFirstBin) {
-      float* q = P2 + p2_index(bin, col);
-      q[0] = v.x;
-      q[2] = v.y;
-    }
+    float* q = P2 + p2_index(bin >= kMelFirstBin ? bin : 256, col);
+    q[0] = v.x;
+    q[2] = v.y;
   }
 };
 
@@ -309,6 +308,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
   // CTA's FFT always overlaps the other's mel / DCT / classifier, was 3.3x SLOWER: 696 vs 212 ms.  Letting the warps
   // whose frame slots lie past the segment end skip the transform of a short last step: 214.7 vs 212.0 ms.)
 
+  // Called by warp 0 only (the bulk copy is issued by thread 0, the < 8-sample tail is copied by lanes 0-6).
   auto issue_load = [&](int step, int buf) {
     const long long start = seg.pcm_start + static_cast<long long>(step) * (kStepFrames * kHop);
     const long long avail = p.pcm_len - start;
@@ -334,12 +334,12 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
     const int nsteps = (n + kStepFrames - 1) / kStepFrames;
     int out_done = (MODE == 0) ? 0 : 2;
     bool dct_pending = false;  // the previous step's log-mel tile still waits for its DCT
-    if (nsteps > 0) issue_load(0, gstep & 1);
+    if (nsteps > 0 && warp == 0) issue_load(0, gstep & 1);
     __syncthreads();
 
     for (int s = 0; s < nsteps; ++s, ++gstep) {
       const int buf = gstep & 1;
-      if (s + 1 < nsteps) issue_load(s + 1, buf ^ 1);
+      if (s + 1 < nsteps && warp == 0) issue_load(s + 1, buf ^ 1);
       mbar_wait(&s_bar[buf], (gstep >> 1) & 1);
 
       // Two split-phase barriers (mbarrier arrive / wait, one arrival per warp) replace CTA-wide bar.syncs, so a warp
