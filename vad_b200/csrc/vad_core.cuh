@@ -339,11 +339,16 @@ VADB_HD void fft_split_store_tw(const V (&xr)[16], const V (&xi)[16], int k1, TW
     V plo, phi;
     split_pair(xr[k2], xi[k2], br, bi, w.x, w.y, plo, phi);
     const int lo = k1 + 16 * k2;
-    store(lo, plo);
-    if (kSink || k2 != 0 || k1 != 0) store(256 - lo, phi);   // thread 0's (0, 256) pair: bin 256 is the sink
+    if constexpr (kSink) {   // addresses are affine in k2: the store keeps per-thread base pointers
+      store.lo(K, plo);
+      store.hi(K, phi);      // thread 0's (0, 256) pair: bin 256 is the sink
+    } else {
+      store(lo, plo);
+      if (k2 != 0 || k1 != 0) store(256 - lo, phi);
+    }
   });
   if constexpr (kSink) {
-    store(k1 == 0 ? 128 : 256, vmuls(4.0f, vfma(xr[8], xr[8], vmul(xi[8], xi[8]))));
+    store.mid(vmuls(4.0f, vfma(xr[8], xr[8], vmul(xi[8], xi[8]))));   // bin 128 on thread 0, sink elsewhere
   } else {
     if (k1 == 0) store(128, vmuls(4.0f, vfma(xr[8], xr[8], vmul(xi[8], xi[8]))));
   }

@@ -171,15 +171,34 @@ __device__ __forceinline__ void warp_fft_quad(const uint32_t* w32a, int delta, f
 }
 // The fused kernels' power tile: pair rows (bins 2q, 2q+1 side by side per column, vad_core.cuh p2_index); bins
 // below the first mel bin are dropped.  Columns col (frame A) and col + 1 (frame B).
+// Thread k1 of a half-warp stores bins k1 + 16 k2 ("lo") and 256 - k1 - 16 k2 ("hi"), k2 = 0 .. 7, plus bin 128 on
+// thread 0.  In the pair tile both families are affine in k2 (+- 8 pair rows per step), so four per-thread pointers
+// computed once per kernel replace all per-store index arithmetic.  Row kP2Rows ("bin 256") is a write-only sink:
+// bins below the first mel bin (k2 == 0, k1 < 10), thread 0's bin 256 and the other threads' "bin 128" go there, which
+// makes every store unconditional.
 struct P2Store {
-  static constexpr bool kHasSink = true;  // row kP2Rows ("bin 256") swallows what the mel never reads
-  float* P2;
-  int col;
-  __device__ __forceinline__ void operator()(int bin, f2 v) const {
-    float* q = P2 + p2_index(bin >= kMelFirstBin ? bin : 256, col);
+  static constexpr bool kHasSink = true;
+  float* lo_base;   // bin k1
+  float* hi_base;   // bin 256 - k1
+  float* lo0;       // bin k1 if it is kept, else the sink
+  float* mid_ptr;   // bin 128 (thread 0) or the sink
+  __device__ __forceinline__ P2Store(float* P2, int col, int k1) {
+    lo_base = P2 + p2_index(k1, col);              // may point below the tile for k1 < 10: only used with k2 >= 1
+    hi_base = P2 + p2_index(256 - k1, col);
+    lo0 = k1 >= kMelFirstBin ? lo_base : P2 + p2_index(256, col);
+    mid_ptr = P2 + p2_index(k1 == 0 ? 128 : 256, col);
+  }
+  static __device__ __forceinline__ void put(float* q, f2 v) {
     q[0] = v.x;
     q[2] = v.y;
   }
+  template <class K> __device__ __forceinline__ void lo(K, f2 v) const {
+    constexpr int k2 = K::value;
+    if constexpr (k2 == 0) put(lo0, v);
+    else put(lo_base + 8 * k2 * kP2Pitch, v);
+  }
+  template <class K> __device__ __forceinline__ void hi(K, f2 v) const { put(hi_base - 8 * K::value * kP2Pitch, v); }
+  __device__ __forceinline__ void mid(f2 v) const { put(mid_ptr, v); }
 };
 
 // Both frames of a warp (lanes 0-15 / 16-31) through the FFT; P column = frame slot fi.
@@ -299,6 +318,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
 
   unsigned gstep = 0;  // loads issued so far by this CTA == steps started; buffer = gstep & 1
   Segment seg;
+  const P2Store p2store(s_P, col_of_halfwarp(warp, h), t);  // this thread's power-store pointers, fixed for the kernel
   __syncthreads();                 // mbarrier inits visible
   warp_arrive(&s_bar[4], lane);    // the power tile starts out free
 
@@ -371,7 +391,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
         // read different banks), P columns 4 warp + 2 h, + 1
         f2* ex = reinterpret_cast<f2*>(s_exch) + (warp * 2 + h) * kExchFrame;
         warp_fft_quad<13>(stage32 + (warp * 4 + h) * (kHop / 2), kHop, ex, s_tw1, s_tw2, lane,
-                          [&] { mbar_wait(&s_bar[4], par); }, P2Store{s_P, col_of_halfwarp(warp, h)});
+                          [&] { mbar_wait(&s_bar[4], par); }, p2store);
       } else {
         mbar_wait(&s_bar[4], par);
       }
@@ -877,7 +897,7 @@ __global__ void __launch_bounds__(kThreads) stream_feed_kernel(const BankParams 
   {
     f2* ex = reinterpret_cast<f2*>(s_exch) + (warp * 2 + h) * kExchFrame;
     const uint32_t* w32 = reinterpret_cast<const uint32_t*>(s_fr + (warp * 4 + h) * kStreamFramePitch);
-    warp_fft_quad<13>(w32, kStreamFramePitch, ex, s_tw1, s_tw2, lane, [] {}, P2Store{s_P, col_of_halfwarp(warp, h)});
+    warp_fft_quad<13>(w32, kStreamFramePitch, ex, s_tw1, s_tw2, lane, [] {}, P2Store(s_P, col_of_halfwarp(warp, h), lane & 15));
   }
   __syncthreads();
   mel2_group_dispatch<kP2Pitch, 32>(warp, s_P + 2 * lane, s_logE + lane);
