@@ -154,7 +154,7 @@ int emul_utterance(const int16_t* pcm, long long n_samples, int feat_mode, float
     // mel + log phase: warp g = filter group, lane = P column
     for (int g = 0; g < 8; ++g)
       for (int lane = 0; lane < 32; ++lane)
-        mel2_group_dispatch<kP2Pitch, 32>(g, P.data() + 2 * lane, logE.data() + lane);
+        mel2_run_dispatch<kP2Pitch, 32>(g, P.data() + 2 * lane, logE.data() + lane);
     // DCT phase: warp w -> coefficients 2w and 2w + 1 (warp 7 idles)
     for (int w = 0; w < 7; ++w)
       for (int lane = 0; lane < 32; ++lane) {

@@ -444,6 +444,51 @@ VADB_HD void mel2_group_dispatch(int g, const float* P2, float* logE) {
     default: mel2_group<7, PITCH2, OPITCH>(P2, logE); break;
   }
 }
+// Load-sharing packed mel: warp g owns the run of consecutive filters kMelRunFirst[g] .. kMelRunLast[g] and walks the
+// pair rows they cover once -- every power pair is loaded a single time (LDS.64) and feeds each filter whose triangle
+// contains it (neighbouring triangles overlap by half: two FFMA2 per load in the interior).  Two accumulator chains per
+// filter; with two or three filters live per row that is four to six independent FFMA2 chains.
+template <int G, int PITCH2, int OPITCH>
+VADB_HD void mel2_run(const float* P2, float* logE) {
+  constexpr int m0 = kMelRunFirst[G], m1 = kMelRunLast[G], nf = m1 - m0 + 1;
+  constexpr int qa = mel_q0(m0), qb = mel_q0(m1) + mel_nq(m1);   // pair rows [qa, qb)
+  f2 acc[nf][2];
+  static_for<0, nf>([&](auto F) { acc[F][0] = mk2(0.0f, 0.0f); acc[F][1] = mk2(0.0f, 0.0f); });
+  static_for<qa, qb>([&](auto Q) {
+    constexpr int q = Q;
+    const float* pp = P2 + (q - kP2FirstRow) * PITCH2;
+    const f2 pv = mk2(pp[0], pp[1]);
+    static_for<0, nf>([&](auto F) {
+      constexpr int m = m0 + F;
+      if constexpr (q >= mel_q0(m) && q < mel_q0(m) + mel_nq(m)) {
+        constexpr int i = q - mel_q0(m), off = mel_qoff(m);
+        const f2 wv = mk2(c_tab.melw2[2 * (off + i)], c_tab.melw2[2 * (off + i) + 1]);
+        acc[F][i & 1] = vfma(pv, wv, acc[F][i & 1]);
+      }
+    });
+    // a filter whose last row this was is finished: log and store it while the others continue
+    static_for<0, nf>([&](auto F) {
+      constexpr int m = m0 + F;
+      if constexpr (q == mel_q0(m) + mel_nq(m) - 1) {
+        const f2 sacc = vadd(acc[F][0], acc[F][1]);
+        logE[m * OPITCH] = log2_energy(sacc.x + sacc.y);
+      }
+    });
+  });
+}
+template <int PITCH2, int OPITCH>
+VADB_HD void mel2_run_dispatch(int g, const float* P2, float* logE) {
+  switch (g) {
+    case 0: mel2_run<0, PITCH2, OPITCH>(P2, logE); break;
+    case 1: mel2_run<1, PITCH2, OPITCH>(P2, logE); break;
+    case 2: mel2_run<2, PITCH2, OPITCH>(P2, logE); break;
+    case 3: mel2_run<3, PITCH2, OPITCH>(P2, logE); break;
+    case 4: mel2_run<4, PITCH2, OPITCH>(P2, logE); break;
+    case 5: mel2_run<5, PITCH2, OPITCH>(P2, logE); break;
+    case 6: mel2_run<6, PITCH2, OPITCH>(P2, logE); break;
+    default: mel2_run<7, PITCH2, OPITCH>(P2, logE); break;
+  }
+}
 // Who owns which column of the 32-frame step.  Half-warp h of warp w carries frame slots 4w + h and 4w + h + 2 (PCM of
 // neighbouring slots is 80 words apart, so the two half-warps read different banks) and stores them in adjacent
 // columns c, c + 1 with c = 2 (w & 3) + 8 h + 16 (w >> 2): the second half-warp's columns are 8 further, i.e. 16

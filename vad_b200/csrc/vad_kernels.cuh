@@ -406,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
       // (a rolled, table-driven mel loop -- one small code body for all warps, weights in shared memory -- was
       // measured 5.8 % slower than these eight straight-line regions: its loads are latency-exposed)
       if (!(VADB_DBG(p) & 2))
-        mel2_group_dispatch<kP2Pitch, 32>(warp, s_P + 2 * lane, s_logE + (s & 1) * kLogEFloats + lane);
+        mel2_run_dispatch<kP2Pitch, 32>(warp, s_P + 2 * lane, s_logE + (s & 1) * kLogEFloats + lane);
       warp_arrive(&s_bar[4], lane);
       const int computed = min((s + 1) * kStepFrames, n);
       const bool block_now = (((s + 1) % kBlk) == 0 || s == nsteps - 1) && !(VADB_DBG(p) & 8);
@@ -900,7 +900,7 @@ __global__ void __launch_bounds__(kThreads) stream_feed_kernel(const BankParams 
     warp_fft_quad<13>(w32, kStreamFramePitch, ex, s_tw1, s_tw2, lane, [] {}, P2Store(s_P, col_of_halfwarp(warp, h), lane & 15));
   }
   __syncthreads();
-  mel2_group_dispatch<kP2Pitch, 32>(warp, s_P + 2 * lane, s_logE + lane);
+  mel2_run_dispatch<kP2Pitch, 32>(warp, s_P + 2 * lane, s_logE + lane);
   __syncthreads();
   // ---- DCT + ring + window features: warp = coefficient (w, w + 8), lane = P column ----------------
   const int slot = slot_of_col(lane);      // stream of this lane inside the CTA
