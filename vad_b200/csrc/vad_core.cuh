@@ -451,6 +451,7 @@ VADB_HD void mel2_group_dispatch(int g, const float* P2, float* logE) {
 template <int G, int PITCH2, int OPITCH>
 VADB_HD void mel2_run(const float* P2, float* logE) {
   constexpr int m0 = kMelRunFirst[G], m1 = kMelRunLast[G], nf = m1 - m0 + 1;
+  if constexpr (nf > 0) {
   constexpr int qa = mel_q0(m0), qb = mel_q0(m1) + mel_nq(m1);   // pair rows [qa, qb)
   f2 acc[nf][2];
   static_for<0, nf>([&](auto F) { acc[F][0] = mk2(0.0f, 0.0f); acc[F][1] = mk2(0.0f, 0.0f); });
@@ -475,6 +476,7 @@ VADB_HD void mel2_run(const float* P2, float* logE) {
       }
     });
   });
+  }  // warps without filters do nothing
 }
 template <int PITCH2, int OPITCH>
 VADB_HD void mel2_run_dispatch(int g, const float* P2, float* logE) {
@@ -536,6 +538,35 @@ VADB_HD void dct_coef2(const float* logE, int p, float& ra, float& rb) {
   const f2 r = vadd(vadd(a0, a2), vadd(a1, a3));
   ra = r.x;
   rb = r.y;
+}
+
+// Two coefficient pairs (p, p + 1) of the same frame from one pass over the 26 log-energies: the loads are shared,
+// the eight FFMA2 chains are those of two dct_coef2 calls (bit-identical results).
+template <int PITCH>
+VADB_HD void dct_coef4(const float* logE, int p, float& ra, float& rb, float& rc, float& rd) {
+  f2 a0 = mk2(0.0f, 0.0f), a1 = a0, a2 = a0, a3 = a0, b0 = a0, b1 = a0, b2 = a0, b3 = a0;
+  const float (*w)[2] = c_tab.dctp[p];
+  const float (*v)[2] = c_tab.dctp[p + 1];
+#pragma unroll
+  for (int n = 0; n < 24; n += 4) {
+    const float e0 = logE[(n + 0) * PITCH], e1 = logE[(n + 1) * PITCH], e2 = logE[(n + 2) * PITCH],
+                e3 = logE[(n + 3) * PITCH];
+    a0 = vfmas(e0, mk2(w[n + 0][0], w[n + 0][1]), a0);
+    b0 = vfmas(e0, mk2(v[n + 0][0], v[n + 0][1]), b0);
+    a1 = vfmas(e1, mk2(w[n + 1][0], w[n + 1][1]), a1);
+    b1 = vfmas(e1, mk2(v[n + 1][0], v[n + 1][1]), b1);
+    a2 = vfmas(e2, mk2(w[n + 2][0], w[n + 2][1]), a2);
+    b2 = vfmas(e2, mk2(v[n + 2][0], v[n + 2][1]), b2);
+    a3 = vfmas(e3, mk2(w[n + 3][0], w[n + 3][1]), a3);
+    b3 = vfmas(e3, mk2(v[n + 3][0], v[n + 3][1]), b3);
+  }
+  const float e24 = logE[24 * PITCH], e25 = logE[25 * PITCH];
+  a0 = vfmas(e24, mk2(w[24][0], w[24][1]), a0);
+  b0 = vfmas(e24, mk2(v[24][0], v[24][1]), b0);
+  a1 = vfmas(e25, mk2(w[25][0], w[25][1]), a1);
+  b1 = vfmas(e25, mk2(v[25][0], v[25][1]), b1);
+  const f2 r = vadd(vadd(a0, a2), vadd(a1, a3)), q = vadd(vadd(b0, b2), vadd(b1, b3));
+  ra = r.x; rb = r.y; rc = q.x; rd = q.y;
 }
 
 VADB_HD float vadb_rsqrt(float v) {

@@ -374,12 +374,18 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
         if (!(VADB_DBG(p) & 4)) {
           const float* le = s_logE + (sd & 1) * kLogEFloats + lane;
           const int col = (sd * kStepFrames + slot_of_col(lane)) % kRing;  // lane = P column
-          if (warp < kRingRows) {  // warp w: coefficients 2w, 2w + 1 -> one 64-bit ring element (warp 7 idles)
+          // Warps 0-3 share the transform, so a column's 26 log-energies are loaded 4 times instead of 7: warps 0-2
+          // take two coefficient pairs each, warp 3 the seventh; the mel runs (tools/gen_tables.py) are sized so that
+          // these warps carry little or no mel work.
+          if (warp < 3) {
+            float ra, rb, rc, rd;
+            dct_coef4<32>(le, 2 * warp, ra, rb, rc, rd);
+            *reinterpret_cast<float2*>(s_ring + ring_idx(4 * warp, col, kRing)) = make_float2(ra, rb);
+            *reinterpret_cast<float2*>(s_ring + ring_idx(4 * warp + 2, col, kRing)) = make_float2(rc, rd);
+          } else if (warp == 3) {
             float ra, rb;
-            dct_coef2<32>(le, warp, ra, rb);
-            float* dst = s_ring + ring_idx(2 * warp, col, kRing);
-            if (2 * warp + 1 < kNCep) *reinterpret_cast<float2*>(dst) = make_float2(ra, rb);
-            else dst[0] = ra;
+            dct_coef2<32>(le, 6, ra, rb);
+            s_ring[ring_idx(12, col, kRing)] = ra;
           }
         }
       };
