@@ -185,8 +185,11 @@ struct P2Store {
   __device__ __forceinline__ P2Store(float* P2, int col, int k1) {
     lo_base = P2 + p2_index(k1, col);              // may point below the tile for k1 < 10: only used with k2 >= 1
     hi_base = P2 + p2_index(256 - k1, col);
-    lo0 = k1 >= kMelFirstBin ? lo_base : P2 + p2_index(256, col);
-    mid_ptr = P2 + p2_index(k1 == 0 ? 128 : 256, col);
+    // every lane of a warp gets its own word of the sink row (k1 + 16 h, h = half-warp = bit 3 of the column):
+    // several lanes storing to one address would be serialised
+    float* sink = P2 + kP2Rows * kP2Pitch + k1 + 2 * (col & 8);
+    lo0 = k1 >= kMelFirstBin ? lo_base : sink;
+    mid_ptr = k1 == 0 ? P2 + p2_index(128, col) : sink;
   }
   static __device__ __forceinline__ void put(float* q, f2 v) {
     q[0] = v.x;
