@@ -52,6 +52,8 @@ constexpr int kOffSeg = kOffBar + 48;                                       // 6
 constexpr int kFusedSmemBytes = kOffSeg + 16;                               // s_seg, s_tmem
 constexpr int kBlockStepsTc = 4;                                            // tensor-core FFN: one M=128 tile
 static_assert(kTcBlobBytes <= kWarps * 2 * kExchFrame * 8 + kP2Bytes, "weight blob must fit exch + P");
+static_assert(kBlockSteps * kStepFrames * kNFeat * 4 + 16 <= kWarps * 2 * kExchFrame * 8 + kP2Bytes,
+              "dataset-row staging tile must fit exch + P");
 static_assert(2 * (kFusedSmemBytes + 1024) <= 233472, "two CTAs per SM");
 
 struct Segment {
@@ -450,26 +452,42 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
           });
           out_done = computed;
         } else if (MODE == 1) {
-          const int last = computed - 3;  // centres out_done .. last
-          float* dst = p.rows + (seg.out_start - p.row_base + (out_done - 2)) * kNFeat;
-          const int first = out_done;
-          flush_flat(dst, (last - out_done + 1) * kNFeat, tid, [&](int j, float (&v)[4], int cnt) {
-            int rr = j / kNFeat, col = j - rr * kNFeat;
-            int grp = col / kNCep, cf = col - grp * kNCep;
+          // Dataset rows [c (13) | d1 (13) | d2 (13)] of centres out_done .. computed - 3 (<= 256): thread = centre
+          // builds its 39 values with the packed window arithmetic and writes them into a staging tile that has the
+          // layout of the output rows (exch + P are idle here; a row is 39 floats = 7 banks apart: conflict free);
+          // the tile then leaves with 128-bit coalesced stores, without any per-element index arithmetic.
+          const int n_valid = computed - 2 - out_done;
+          if (n_valid > 0) {  // block-uniform
+            float* dst = p.rows + (seg.out_start - p.row_base + (out_done - 2)) * kNFeat;
+            // staging starts at the same offset within 16 bytes as dst, so 128-bit chunks line up on both sides
+            float* stage = reinterpret_cast<float*>(smem + kOffExch) + ((reinterpret_cast<uintptr_t>(dst) & 15u) >> 2);
+            if (tid < n_valid) {
+              float xa[24], xb[24];
+              window_features_pairs<0, 4, kRing, 24>(s_ring, out_done + tid, 1, xa);
+              window_features_pairs<4, 7, kRing, 24>(s_ring, out_done + tid, 1, xb);
+              float* row = stage + tid * kNFeat;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if (i < cnt) {
-                const int c = first + rr;
-                const float* row = s_ring + ring_idx(cf, 0, kRing);  // element stride 2
-                const float c2 = row[2 * (c % kRing)];
-                v[i] = grp == 0 ? c2
-                     : grp == 1 ? row[2 * ((c + 1) % kRing)] - row[2 * ((c - 1) % kRing)]
-                                : (row[2 * ((c + 2) % kRing)] - c2) - (c2 - row[2 * ((c - 2) % kRing)]);
+              for (int g = 0; g < 3; ++g) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) row[g * kNCep + k] = xa[6 * (k >> 1) + 2 * g + (k & 1)];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) row[g * kNCep + 8 + k] = xb[6 * (k >> 1) + 2 * g + (k & 1)];
               }
-              if (++cf == kNCep) { cf = 0; if (++grp == 3) { grp = 0; ++rr; } }
             }
-          });
-          out_done = max(out_done, last + 1);
+            __syncthreads();
+            flush_flat(dst, n_valid * kNFeat, tid, [&](int j, float (&v)[4], int cnt) {
+              if (cnt == 4) {
+                const float4 q = *reinterpret_cast<const float4*>(stage + j);
+                v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (i < cnt) v[i] = stage[j + i];
+              }
+            });
+            __syncthreads();  // the next FFT phase rewrites exch / P
+          }
+          out_done = max(out_done, computed - 2);
         } else if (!TC) {
           const int c = out_done + tid;
           if (c <= computed - 3) {
