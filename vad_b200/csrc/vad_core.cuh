@@ -338,11 +338,11 @@ VADB_HD void fft_split_store_tw(const V (&xr)[16], const V (&xi)[16], int k1, TW
     const cf2 w = tw2(K);  // W512^(k1 + 16 k2)
     V plo, phi;
     split_pair(xr[k2], xi[k2], br, bi, w.x, w.y, plo, phi);
-    const int lo = k1 + 16 * k2;
     if constexpr (kSink) {   // addresses are affine in k2: the store keeps per-thread base pointers
       store.lo(K, plo);
       store.hi(K, phi);      // thread 0's (0, 256) pair: bin 256 is the sink
     } else {
+      const int lo = k1 + 16 * k2;
       store(lo, plo);
       if (k2 != 0 || k1 != 0) store(256 - lo, phi);
     }
