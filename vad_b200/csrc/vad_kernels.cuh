@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 2) fused_kernel(const __grid_constan
   }
 
   unsigned gstep = 0;  // loads issued so far by this CTA == steps started; buffer = gstep & 1
-  Segment seg;
+  Segment seg{};
   const P2Store p2store(s_P, col_of_halfwarp(warp, h), t);  // this thread's power-store pointers, fixed for the kernel
   __syncthreads();                 // mbarrier inits visible
   warp_arrive(&s_bar[4], lane);    // the power tile starts out free
@@ -936,7 +936,7 @@ __global__ void __launch_bounds__(kThreads) stream_feed_kernel(const BankParams 
   const long long ns = p.n_streams;
   const int fed = live ? p.fed[st] : 0;    // chunks fed before this one
   const int frame = fed - 2;               // index of the frame completed by this chunk (< 0: none yet)
-  const bool classify = frame >= 5;        // ring holds frames frame-5 .. frame-1: classify frame-3
+  // (a row is classified once frame >= 5: the ring then holds frames frame-5 .. frame-1 and frame-3 is the centre)
 #pragma unroll
   for (int rep = 0; rep < 2; ++rep) {
     const int k = warp + 8 * rep;
