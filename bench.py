@@ -36,8 +36,8 @@ FLOP_PER_FRAME_MFCC = 13878    # MFCC-only subtotal (cfg2); dataset rows add 39 
 BYTES_PER_FRAME_FUSED = 321    # 160 int16 in + 1 label out
 FP32_NOMINAL_TFLOPS = 74.4     # 148 SM x 128 lanes x 2 x 1.965 GHz (fallback denominator)
 # dram__bytes_read.sum + dram__bytes_write.sum of fused_kernel<2,2> from the committed `ncu --set full`
-# capture (profiles/r2_fused_kernel_2_2_ncu_raw.csv: 5.8275 GB + 0.0226 GB for 17.874 M frames)
-NCU_DRAM_BYTES_PER_FRAME = (5.827530e9 + 22.635520e6) / 17874000.0
+# capture (profiles/r3_fused_kernel_2_2_ncu_raw.csv: 5.8250 GB + 0.0235 GB for 17.874 M frames)
+NCU_DRAM_BYTES_PER_FRAME = (5.824964e9 + 23.526144e6) / 17874000.0
 
 
 def parse_args():
@@ -536,7 +536,7 @@ def main():
     hbm_ach = frames * BYTES_PER_FRAME_FUSED / kern_s / 1e9
     roofline = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": frames * NCU_DRAM_BYTES_PER_FRAME if a.ffn_impl != "fp32" else None,
-                "traffic_note": "bytes per launch = frames x 327.3 B/frame from the ncu capture in profiles/ "
+                "traffic_note": "bytes per launch = frames x %.1f B/frame from the ncu capture in profiles/ (r3) " % NCU_DRAM_BYTES_PER_FRAME +
                                 "(algorithmic 321 B/frame: no re-reads)",
                 "kernel": "%s (MFCC+FFN VAD, FFN on %s)" % (
                     {"tc16": "fused_kernel<2,2>", "tc": "fused_kernel<2,1>", "fp32": "fused_kernel<2,0>"}[a.ffn_impl],

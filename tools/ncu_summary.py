@@ -2,7 +2,7 @@
 """Turn an .ncu-rep (read here, no GPU needed) into the small evidence files kept under profiles/:
    python tools/ncu_summary.py gpurun_out/r2_prof_k22.ncu-rep profiles/r2_fused_kernel_2_2
 writes <out>_ncu_raw.csv (selected raw metrics) and <out>_phases.txt (time / instruction share and top stalls of
-every region between block barriers, from the source page; needs -lineinfo / --import-source)."""
+every region between block barriers / mbarrier waits, from the source page; needs -lineinfo / --import-source)."""
 import collections
 import csv
 import io
@@ -41,10 +41,12 @@ def main():
     stalls = [h for h in h2 if h.startswith("stall_")]
     tot = sum(int(r[ix["# Samples"]] or 0) for r in data)
     toti = sum(int(r[ix["Instructions Executed"]] or 0) for r in data)
-    lines = ["kernel: %s" % src[0][1], "regions between BAR.SYNC / EXIT (SASS instruction index range):"]
+    lines = ["kernel: %s" % src[0][1],
+             "regions between BAR.SYNC / mbarrier try_wait (SYNCS...TRYWAIT) / EXIT (SASS instruction index range):"]
     start = 0
     for i, r in enumerate(data):
-        if "BAR.SYNC" in r[ix["Source"]] or "EXIT" in r[ix["Source"]] or i == len(data) - 1:
+        if ("BAR.SYNC" in r[ix["Source"]] or "TRYWAIT" in r[ix["Source"]] or "EXIT" in r[ix["Source"]]
+                or i == len(data) - 1):
             a, b = start, i
             start = i + 1
             s = sum(int(x[ix["# Samples"]] or 0) for x in data[a:b + 1])
