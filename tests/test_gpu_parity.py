@@ -431,6 +431,32 @@ def test_stm_segments_gather(env, tmp_path):
     assert rows_close(rows, want)
 
 
+def test_every_row_of_a_ragged_batch_mfcc_and_dataset_modes(env):
+    """All rows (not a sample) of a ragged batch in both row modes against the oracle: utterances from below one step to
+    several block phases long, so the flushes start at every alignment of the output pointer within 16 bytes (rows are
+    13 / 39 floats) and the staged dataset flush runs with 1 .. 256 valid centres."""
+    from vad_b200 import batch
+    h, _ = env
+    lens = [400 + 160 * k for k in (5, 6, 7, 8, 31, 32, 33, 34, 127, 130, 255, 258, 259, 300, 611)] + [401, 40123, 99999]
+    utts_ = [synth_utterance(29, i, n) for i, n in enumerate(lens)]
+    rows39 = batch.mfcc_batch(utts_, deltas=True, handle=h)
+    rows13 = batch.mfcc_batch(utts_, deltas=False, handle=h)
+    starts = set()
+    acc = 0
+    for u, r39, r13 in zip(utts_, rows39, rows13):
+        c = rm.mfcc_utterance(u)
+        want = rm.dataset_features(c)
+        got = r39.cpu().numpy()
+        assert got.shape == want.shape, (len(u), got.shape, want.shape)
+        if want.shape[0]:
+            assert rows_close(got, want), (len(u), float(np.abs(got - want).max()))
+        g13 = r13.cpu().numpy()
+        assert g13.shape == c.shape and mfcc_close(g13, c), len(u)
+        starts.add((acc * 39 * 4) % 16)
+        acc += want.shape[0]
+    assert starts == {0, 4, 8, 12}   # the batch really covers every start alignment of the dataset rows
+
+
 def test_two_handles_with_different_weights(env):
     """Constant-bank ownership switches between handles (and FFN implementations) without mixing weights."""
     import torch
