@@ -36,8 +36,8 @@ FLOP_PER_FRAME_MFCC = 13878    # MFCC-only subtotal (cfg2); dataset rows add 39 
 BYTES_PER_FRAME_FUSED = 321    # 160 int16 in + 1 label out
 FP32_NOMINAL_TFLOPS = 74.4     # 148 SM x 128 lanes x 2 x 1.965 GHz (fallback denominator)
 # dram__bytes_read.sum + dram__bytes_write.sum of fused_kernel<2,2> from the committed `ncu --set full`
-# capture (profiles/r3_fused_kernel_2_2_ncu_raw.csv: 5.8250 GB + 0.0235 GB for 17.874 M frames)
-NCU_DRAM_BYTES_PER_FRAME = (5.824964e9 + 23.526144e6) / 17874000.0
+# capture (profiles/r3_fused_kernel_2_2_ncu_raw.csv: 5.8241 GB + 0.0227 GB for 17.874 M frames)
+NCU_DRAM_BYTES_PER_FRAME = (5.824133e9 + 22.738688e6) / 17874000.0
 
 
 def parse_args():
