@@ -1,4 +1,6 @@
 // tools/experiments/async_and_split_kernels.cuh -- NOT part of the product build.
+// A snapshot written against the headers of the round-2 mid-session build (warp_fft_quad / P2Store / ring layout have
+// changed since: it documents the two designs and their numbers, it is not meant to compile against today's csrc/).
 //
 // Two restructurings of the fused VAD kernel that were built, verified (all 129 GPU parity tests green through
 // the C ABI) and measured on a B200 in round 2, and lost to the phase-synchronous fused_kernel<2,2>:
