@@ -8,10 +8,9 @@
 //   a <- rho a + (1 - rho) g^2;  u = g sqrt(d + eps) / sqrt(a + eps);  theta <- theta - lr u;  d <- rho d + (1 - rho) u^2
 //
 // Two kernels per step, both deterministic (no floating-point atomics):
-//   ffn_train_grad_kernel   one CTA = 128 batch rows.  Forward and backward per row (thread = row, weights broadcast
-//                           from shared memory, activations / deltas parked in shared memory with odd pitches), then
-//                           the weight gradients of the tile as K x N dot products over the 128 rows (thread = output
-//                           entries) -> per-CTA partial gradient + partial loss in global memory.
+//   ffn_train_grad_kernel  persistent CTAs (256 threads) walk tiles of 128 batch rows: forward, deltas and weight
+//                           gradients as register-tiled products over transposed shared-memory tiles (below); weight
+//                           gradients stay in registers across a CTA's tiles -> one partial gradient + partial loss per CTA.
 //   ffn_train_update_kernel thread = parameter: sums the partials in CTA order, applies Adadelta in place.
 #pragma once
 
@@ -27,130 +26,256 @@ constexpr int kNParams = kNFeat * kH1 + kH1 + kH1 * kH2 + kH2 + kH2 * kH3 + kH3 
 constexpr int kOffW1 = 0, kOffB1 = kOffW1 + kNFeat * kH1, kOffW2 = kOffB1 + kH1, kOffB2 = kOffW2 + kH1 * kH2,
               kOffW3 = kOffB2 + kH2, kOffB3 = kOffW3 + kH2 * kH3, kOffW4 = kOffB3 + kH3, kOffB4 = kOffW4 + kH3 * kNCls;
 static_assert(kOffB4 + kNCls == kNParams, "layout");
-// shared-memory pitches (floats), all odd: thread r touching [r * pitch + k] is bank-conflict free
-constexpr int kPX = 39, kPH1 = 65, kPH2 = 33, kPH3 = 17, kPD4 = 5;
-constexpr int kTrainSmemFloats = kNParams + 1 + kTrainRows * (kPX + 2 * kPH1 + 2 * kPH2 + 2 * kPH3 + kPD4) + 8;
-constexpr int kTrainSmemBytes = kTrainSmemFloats * 4;
+// ---- gradient kernel: register-tiled, persistent --------------------------------------------------------------------
+// One CTA (256 threads) walks tiles of 128 batch rows.  Activations and deltas live in shared memory TRANSPOSED
+// ([feature][128 rows]), so every product A^T B, D W^T and A^T D of the step is the same register-tiled loop: a thread
+// owns RM rows x CN columns (or 4 x 4 weight-gradient entries), reads its operands with 64 / 128-bit loads and does
+// 8-10 FMAs per load instead of one FMA per two loads.  Each activation buffer carries a row of ones after its
+// features, so the bias gradients fall out of the weight-gradient tiles.  Weight gradients stay in registers across
+// the CTA's tiles and are written once as this CTA's partial (summed by ffn_train_update_kernel in CTA order):
+// deterministic for a given grid, no floating-point atomics.
+constexpr int kTr2Threads = 256;
+constexpr int kTr2KX = 40, kTr2KH1 = 68, kTr2KH2 = 36, kTr2KH3 = 20;     // rows of X^T / H^T incl. the ones row, padded to 4
+constexpr int kTr2OffWT2 = ((kNParams + 3) / 4) * 4;                      // WT2[n][k] = W2[k][n]: [32][64]
+constexpr int kTr2OffWT3 = kTr2OffWT2 + kH2 * kH1;                        // [16][32]
+constexpr int kTr2OffWT4 = kTr2OffWT3 + kH3 * kH2;                        // [4][16], row 3 zero
+constexpr int kTr2OffX = kTr2OffWT4 + 4 * kH3;
+constexpr int kTr2OffH1 = kTr2OffX + kTr2KX * kTrainRows;
+constexpr int kTr2OffH2 = kTr2OffH1 + kTr2KH1 * kTrainRows;
+constexpr int kTr2OffH3 = kTr2OffH2 + kTr2KH2 * kTrainRows;
+constexpr int kTr2OffD1 = kTr2OffH3 + kTr2KH3 * kTrainRows;               // deltas [N][128]; D1 doubles as the load staging
+constexpr int kTr2OffD2 = kTr2OffD1 + kH1 * kTrainRows;
+constexpr int kTr2OffD3 = kTr2OffD2 + kH2 * kTrainRows;
+constexpr int kTr2OffD4 = kTr2OffD3 + kH3 * kTrainRows;                   // [4][128], row 3 zero
+constexpr int kTr2OffLoss = kTr2OffD4 + 4 * kTrainRows;
+constexpr int kTrain2SmemBytes = (kTr2OffLoss + 8) * 4;
+static_assert(kTrain2SmemBytes <= 227 * 1024, "training tiles must fit one CTA's shared memory");
+static_assert(kTrainRows * 41 <= kH1 * kTrainRows, "row-major staging of an input tile fits the D1 buffer");
 
-// dW[k][n] = sum_r a[r][k] d[r][n] (and db[n] = sum_r d[r][n]) of one layer -> partial gradient of this CTA
-template <int K, int N, int PA, int PD>
-__device__ __forceinline__ void train_layer_grad(const float* a, const float* d, int rows, float* gW, float* gb) {
-  for (int o = threadIdx.x; o < K * N; o += kTrainRows) {
-    const int k = o / N, n = o - k * N;
-    float s0 = 0.0f, s1 = 0.0f;
-    int r = 0;
-    for (; r + 1 < rows; r += 2) {
-      s0 = fmaf(a[r * PA + k], d[r * PD + n], s0);
-      s1 = fmaf(a[(r + 1) * PA + k], d[(r + 1) * PD + n], s1);
+// C^T[n][r] = sum_k At[k][r] B[k][n] over one 128-row tile; thread tile RM rows x CN columns; epi(row0, col0, acc).
+template <int K, int N, int RM, int CN, class EPI>
+__device__ __forceinline__ void tr2_gemm(const float* __restrict__ At, const float* __restrict__ B, EPI&& epi) {
+  constexpr int CG = N / CN;
+  static_assert((kTrainRows / RM) * CG == kTr2Threads && RM % 4 == 0 && (CN == 2 || CN == 4), "thread tiling");
+  const int tc = threadIdx.x % CG, tr = threadIdx.x / CG;
+  float acc[RM][CN];
+#pragma unroll
+  for (int i = 0; i < RM; ++i)
+#pragma unroll
+    for (int j = 0; j < CN; ++j) acc[i][j] = 0.0f;
+  const float* ap = At + tr * RM;
+  const float* bp = B + tc * CN;
+#pragma unroll 4
+  for (int k = 0; k < K; ++k) {
+    float a[RM], b[CN];
+#pragma unroll
+    for (int i = 0; i < RM; i += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(ap + k * kTrainRows + i);
+      a[i] = v.x; a[i + 1] = v.y; a[i + 2] = v.z; a[i + 3] = v.w;
     }
-    if (r < rows) s0 = fmaf(a[r * PA + k], d[r * PD + n], s0);
-    gW[o] = s0 + s1;
+    if constexpr (CN == 4) {
+      const float4 v = *reinterpret_cast<const float4*>(bp + k * N);
+      b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
+    } else {
+      const float2 v = *reinterpret_cast<const float2*>(bp + k * N);
+      b[0] = v.x; b[1] = v.y;
+    }
+#pragma unroll
+    for (int i = 0; i < RM; ++i)
+#pragma unroll
+      for (int j = 0; j < CN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
   }
-  for (int n = threadIdx.x; n < N; n += kTrainRows) {
-    float s = 0.0f;
-    for (int r = 0; r < rows; ++r) s += d[r * PD + n];
-    gb[n] = s;
+  epi(tr * RM, tc * CN, acc);
+}
+// forward epilogue: + bias, ReLU -> H^T[col][row0 ..]
+template <int RM, int CN>
+__device__ __forceinline__ void tr2_store_relu(float* Ht, const float* bias, int row0, int col0, float (&acc)[RM][CN]) {
+#pragma unroll
+  for (int j = 0; j < CN; ++j) {
+    const float b = bias[col0 + j];
+#pragma unroll
+    for (int i = 0; i < RM; i += 4)
+      *reinterpret_cast<float4*>(Ht + (col0 + j) * kTrainRows + row0 + i) =
+          make_float4(fmaxf(acc[i][j] + b, 0.0f), fmaxf(acc[i + 1][j] + b, 0.0f), fmaxf(acc[i + 2][j] + b, 0.0f),
+                      fmaxf(acc[i + 3][j] + b, 0.0f));
   }
 }
+// backward epilogue: delta = activation > 0 ? acc : 0 -> D^T[col][row0 ..]
+template <int RM, int CN>
+__device__ __forceinline__ void tr2_store_delta(float* Dt, const float* Ht, int row0, int col0, float (&acc)[RM][CN]) {
+#pragma unroll
+  for (int j = 0; j < CN; ++j)
+#pragma unroll
+    for (int i = 0; i < RM; i += 4) {
+      const float4 hh = *reinterpret_cast<const float4*>(Ht + (col0 + j) * kTrainRows + row0 + i);
+      *reinterpret_cast<float4*>(Dt + (col0 + j) * kTrainRows + row0 + i) =
+          make_float4(hh.x > 0.0f ? acc[i][j] : 0.0f, hh.y > 0.0f ? acc[i + 1][j] : 0.0f,
+                      hh.z > 0.0f ? acc[i + 2][j] : 0.0f, hh.w > 0.0f ? acc[i + 3][j] : 0.0f);
+    }
+}
 
-__global__ void __launch_bounds__(kTrainRows) ffn_train_grad_kernel(const float* params, const float* x,
-                                                                    const uint8_t* y, long long n_rows, float inv_b,
-                                                                    float* partial /*[grid][kNParams + 1]*/) {
+// A weight-gradient tile: 4 rows of an activation buffer (k0 ..) x 4 rows of a delta buffer (n0 ..), summed over rows.
+// 337 tiles over 256 threads: two rounds, the second 32 % full.  (4 x 2 tiles in three rounds balance better and were
+// measured 8 % slower: 50 % more shared-memory loads per FMA.)
+struct Tr2GradTile {
+  int a_off, d_off;   // shared-memory offsets (floats) of the 4 activation rows / 4 delta rows
+  int layer, k0, n0;  // where the 16 sums go; layer < 0: no tile
+};
+__device__ __forceinline__ Tr2GradTile tr2_grad_tile(int t) {
+  // layer 1: 10 x 16 tiles, layer 2: 17 x 8, layer 3: 9 x 4, layer 4: 5 x 1
+  Tr2GradTile g{0, 0, -1, 0, 0};
+  if (t < 160) { g.layer = 0; g.k0 = 4 * (t / 16); g.n0 = 4 * (t % 16); g.a_off = kTr2OffX; g.d_off = kTr2OffD1; }
+  else if (t < 296) { t -= 160; g.layer = 1; g.k0 = 4 * (t / 8); g.n0 = 4 * (t % 8); g.a_off = kTr2OffH1; g.d_off = kTr2OffD2; }
+  else if (t < 332) { t -= 296; g.layer = 2; g.k0 = 4 * (t / 4); g.n0 = 4 * (t % 4); g.a_off = kTr2OffH2; g.d_off = kTr2OffD3; }
+  else if (t < 337) { t -= 332; g.layer = 3; g.k0 = 4 * t; g.n0 = 0; g.a_off = kTr2OffH3; g.d_off = kTr2OffD4; }
+  g.a_off += g.k0 * kTrainRows;
+  g.d_off += g.n0 * kTrainRows;
+  return g;
+}
+__device__ __forceinline__ void tr2_grad_accumulate(const float* sm, const Tr2GradTile& g, float (&acc)[4][4]) {
+  const float* a = sm + g.a_off;
+  const float* d = sm + g.d_off;
+  // the eight lanes of a quarter-warp own tiles whose rows start a multiple of 128 floats apart (the same banks), so
+  // each lane walks the 128 batch rows from its own starting group of four: conflict-free 128-bit loads
+  const int rot = 4 * (threadIdx.x & 7);
+#pragma unroll 2
+  for (int rr = 0; rr < kTrainRows; rr += 4) {
+    const int r = (rr + rot) & (kTrainRows - 1);
+    float4 av[4], dv[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      av[i] = *reinterpret_cast<const float4*>(a + i * kTrainRows + r);
+      dv[i] = *reinterpret_cast<const float4*>(d + i * kTrainRows + r);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        acc[i][j] = fmaf(av[i].w, dv[j].w, fmaf(av[i].z, dv[j].z, fmaf(av[i].y, dv[j].y, fmaf(av[i].x, dv[j].x, acc[i][j]))));
+  }
+}
+__device__ __forceinline__ void tr2_grad_write(float* g, const Tr2GradTile& t, const float (&acc)[4][4]) {
+  if (t.layer < 0) return;
+  const int K = t.layer == 0 ? kNFeat : t.layer == 1 ? kH1 : t.layer == 2 ? kH2 : kH3;
+  const int N = t.layer == 0 ? kH1 : t.layer == 1 ? kH2 : t.layer == 2 ? kH3 : kNCls;
+  const int ow = t.layer == 0 ? kOffW1 : t.layer == 1 ? kOffW2 : t.layer == 2 ? kOffW3 : kOffW4;
+  const int ob = t.layer == 0 ? kOffB1 : t.layer == 1 ? kOffB2 : t.layer == 2 ? kOffB3 : kOffB4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = t.k0 + i, n = t.n0 + j;
+      if (n < N) {
+        if (k < K) g[ow + k * N + n] = acc[i][j];
+        else if (k == K) g[ob + n] = acc[i][j];   // the row of ones: bias gradient
+      }
+    }
+}
+
+__global__ void __launch_bounds__(kTr2Threads, 1) ffn_train_grad_kernel(const float* __restrict__ params,
+                                                                         const float* __restrict__ x,
+                                                                         const uint8_t* __restrict__ y, long long n_rows,
+                                                                         float inv_b, float* partial /*[grid][kNParams + 1]*/) {
   extern __shared__ __align__(16) float sm[];
-  float* w = sm;                                   // parameters
-  float* sx = w + kNParams + 1;                    // [rows][39]
-  float* sh1 = sx + kTrainRows * kPX;              // activations (post-ReLU)
-  float* sh2 = sh1 + kTrainRows * kPH1;
-  float* sh3 = sh2 + kTrainRows * kPH2;
-  float* sd1 = sh3 + kTrainRows * kPH3;            // deltas (dloss / dpre-activation)
-  float* sd2 = sd1 + kTrainRows * kPH1;
-  float* sd3 = sd2 + kTrainRows * kPH2;
-  float* sd4 = sd3 + kTrainRows * kPH3;
-  float* sloss = sd4 + kTrainRows * kPD4;
+  float* w = sm;
   const int tid = threadIdx.x;
-  for (int i = tid; i < kNParams; i += kTrainRows) w[i] = params[i];
-  const long long row0 = static_cast<long long>(blockIdx.x) * kTrainRows;
-  const int rows = static_cast<int>(min(static_cast<long long>(kTrainRows), n_rows - row0));
-  for (int i = tid; i < rows * kNFeat; i += kTrainRows) {            // coalesced tile load
-    const int r = i / kNFeat, k = i - r * kNFeat;
-    sx[r * kPX + k] = x[(row0 + r) * kNFeat + k];
+  // parameters, transposed copies for the delta products, constant rows (ones / zero padding)
+  for (int i = tid; i < kNParams; i += kTr2Threads) w[i] = params[i];
+  for (int i = tid; i < kH2 * kH1; i += kTr2Threads) sm[kTr2OffWT2 + i] = params[kOffW2 + (i % kH1) * kH2 + i / kH1];
+  for (int i = tid; i < kH3 * kH2; i += kTr2Threads) sm[kTr2OffWT3 + i] = params[kOffW3 + (i % kH2) * kH3 + i / kH2];
+  for (int i = tid; i < 4 * kH3; i += kTr2Threads)
+    sm[kTr2OffWT4 + i] = i / kH3 < kNCls ? params[kOffW4 + (i % kH3) * kNCls + i / kH3] : 0.0f;
+  for (int i = tid; i < kTrainRows; i += kTr2Threads) {
+    sm[kTr2OffX + kNFeat * kTrainRows + i] = 1.0f;                      // X^T row 39
+    for (int k = kH1; k < kTr2KH1; ++k) sm[kTr2OffH1 + k * kTrainRows + i] = k == kH1 ? 1.0f : 0.0f;
+    for (int k = kH2; k < kTr2KH2; ++k) sm[kTr2OffH2 + k * kTrainRows + i] = k == kH2 ? 1.0f : 0.0f;
+    for (int k = kH3; k < kTr2KH3; ++k) sm[kTr2OffH3 + k * kTrainRows + i] = k == kH3 ? 1.0f : 0.0f;
+    sm[kTr2OffD4 + 3 * kTrainRows + i] = 0.0f;
   }
-  __syncthreads();
-  float loss = 0.0f;
-  if (tid < rows) {
-    const int r = tid;
+  const Tr2GradTile g0 = tr2_grad_tile(tid), g1 = tr2_grad_tile(tid + kTr2Threads);
+  float acc0[4][4], acc1[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc0[i][j] = acc1[i][j] = 0.0f;
+  float loss_acc = 0.0f;   // thread 0 only: tile losses in tile order
+  float* X = sm + kTr2OffX;
+  float* H1 = sm + kTr2OffH1;
+  float* H2 = sm + kTr2OffH2;
+  float* H3 = sm + kTr2OffH3;
+  float* D1 = sm + kTr2OffD1;
+  float* D2 = sm + kTr2OffD2;
+  float* D3 = sm + kTr2OffD3;
+  float* D4 = sm + kTr2OffD4;
+  float* sloss = sm + kTr2OffLoss;
+  const long long n_tiles = (n_rows + kTrainRows - 1) / kTrainRows;
+  for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const long long row0 = tile * kTrainRows;
+    const int rows = static_cast<int>(min(static_cast<long long>(kTrainRows), n_rows - row0));
+    __syncthreads();   // previous tile's gradient pass is done with every buffer (also orders the set-up above)
+    // coalesced load into a row-major staging tile (pitch 41: odd), then transpose into X^T; rows >= rows are zero
+    float* stage = D1;
+    for (int i = tid; i < kTrainRows * kNFeat; i += kTr2Threads) {
+      const int r = i / kNFeat, k = i - r * kNFeat;
+      stage[r * 41 + k] = r < rows ? x[row0 * kNFeat + i] : 0.0f;
+    }
+    __syncthreads();
+    for (int i = tid; i < kTrainRows * kNFeat; i += kTr2Threads) {
+      const int k = i / kTrainRows, r = i - k * kTrainRows;
+      X[k * kTrainRows + r] = stage[r * 41 + k];
+    }
+    __syncthreads();
     // ---- forward (learning/ffn_trainer.py:106-116) ----
-    for (int o = 0; o < kH1; ++o) {
-      float s = w[kOffB1 + o];
-#pragma unroll 13
-      for (int i = 0; i < kNFeat; ++i) s = fmaf(sx[r * kPX + i], w[kOffW1 + i * kH1 + o], s);
-      sh1[r * kPH1 + o] = fmaxf(s, 0.0f);
-    }
-    for (int o = 0; o < kH2; ++o) {
-      float s = w[kOffB2 + o];
-#pragma unroll 16
-      for (int i = 0; i < kH1; ++i) s = fmaf(sh1[r * kPH1 + i], w[kOffW2 + i * kH2 + o], s);
-      sh2[r * kPH2 + o] = fmaxf(s, 0.0f);
-    }
-    for (int o = 0; o < kH3; ++o) {
-      float s = w[kOffB3 + o];
-#pragma unroll 16
-      for (int i = 0; i < kH2; ++i) s = fmaf(sh2[r * kPH2 + i], w[kOffW3 + i * kH3 + o], s);
-      sh3[r * kPH3 + o] = fmaxf(s, 0.0f);
-    }
-    float lg[kNCls];
+    tr2_gemm<kNFeat, kH1, 8, 4>(X, w + kOffW1, [&](int r0, int c0, float (&a)[8][4]) { tr2_store_relu<8, 4>(H1, w + kOffB1, r0, c0, a); });
+    __syncthreads();
+    tr2_gemm<kH1, kH2, 8, 2>(H1, w + kOffW2, [&](int r0, int c0, float (&a)[8][2]) { tr2_store_relu<8, 2>(H2, w + kOffB2, r0, c0, a); });
+    __syncthreads();
+    tr2_gemm<kH2, kH3, 4, 2>(H2, w + kOffW3, [&](int r0, int c0, float (&a)[4][2]) { tr2_store_relu<4, 2>(H3, w + kOffB3, r0, c0, a); });
+    __syncthreads();
+    // ---- layer 4, softmax, categorical cross-entropy, dlogits: thread = row ----
+    float loss = 0.0f;
+    if (tid < kTrainRows) {
+      const int r = tid;
+      float lg[kNCls];
 #pragma unroll
-    for (int o = 0; o < kNCls; ++o) {
-      float s = w[kOffB4 + o];
+      for (int o = 0; o < kNCls; ++o) lg[o] = w[kOffB4 + o];
 #pragma unroll
-      for (int i = 0; i < kH3; ++i) s = fmaf(sh3[r * kPH3 + i], w[kOffW4 + i * kNCls + o], s);
-      lg[o] = s;
-    }
-    // ---- softmax + categorical cross-entropy ----
-    const float mx = fmaxf(lg[0], fmaxf(lg[1], lg[2]));
-    const float e0 = expf(lg[0] - mx), e1 = expf(lg[1] - mx), e2 = expf(lg[2] - mx);
-    const float inv = 1.0f / (e0 + e1 + e2);
-    const float p[kNCls] = {e0 * inv, e1 * inv, e2 * inv};
-    const int cls = y[row0 + r];
-    const float pc = fminf(fmaxf(cls == 0 ? p[0] : cls == 1 ? p[1] : p[2], 1e-7f), 1.0f - 1e-7f);
-    loss = -logf(pc);
-    // ---- backward ----
-    float d4[kNCls];
+      for (int i = 0; i < kH3; ++i) {
+        const float hv = H3[i * kTrainRows + r];
 #pragma unroll
-    for (int o = 0; o < kNCls; ++o) {
-      d4[o] = (p[o] - (o == cls ? 1.0f : 0.0f)) * inv_b;
-      sd4[r * kPD4 + o] = d4[o];
-    }
-    for (int i = 0; i < kH3; ++i) {
-      float s = 0.0f;
+        for (int o = 0; o < kNCls; ++o) lg[o] = fmaf(hv, w[kOffW4 + i * kNCls + o], lg[o]);
+      }
+      const float mx = fmaxf(lg[0], fmaxf(lg[1], lg[2]));
+      const float e0 = expf(lg[0] - mx), e1 = expf(lg[1] - mx), e2 = expf(lg[2] - mx);
+      const float inv = 1.0f / (e0 + e1 + e2);
+      const float p[kNCls] = {e0 * inv, e1 * inv, e2 * inv};
+      const bool live = r < rows;
+      const int cls = live ? y[row0 + r] : 0;
+      const float pc = fminf(fmaxf(cls == 0 ? p[0] : cls == 1 ? p[1] : p[2], 1e-7f), 1.0f - 1e-7f);
+      loss = live ? -logf(pc) : 0.0f;
 #pragma unroll
-      for (int o = 0; o < kNCls; ++o) s = fmaf(d4[o], w[kOffW4 + i * kNCls + o], s);
-      sd3[r * kPH3 + i] = sh3[r * kPH3 + i] > 0.0f ? s : 0.0f;
+      for (int o = 0; o < kNCls; ++o) D4[o * kTrainRows + r] = live ? (p[o] - (o == cls ? 1.0f : 0.0f)) * inv_b : 0.0f;
     }
-    for (int i = 0; i < kH2; ++i) {
-      float s = 0.0f;
 #pragma unroll
-      for (int o = 0; o < kH3; ++o) s = fmaf(sd3[r * kPH3 + o], w[kOffW3 + i * kH3 + o], s);
-      sd2[r * kPH2 + i] = sh2[r * kPH2 + i] > 0.0f ? s : 0.0f;
-    }
-    for (int i = 0; i < kH1; ++i) {
-      float s = 0.0f;
-#pragma unroll 16
-      for (int o = 0; o < kH2; ++o) s = fmaf(sd2[r * kPH2 + o], w[kOffW2 + i * kH2 + o], s);
-      sd1[r * kPH1 + i] = sh1[r * kPH1 + i] > 0.0f ? s : 0.0f;
-    }
+    for (int o = 16; o > 0; o >>= 1) loss += __shfl_down_sync(0xffffffffu, loss, o);
+    if ((tid & 31) == 0) sloss[tid >> 5] = loss;
+    __syncthreads();
+    if (tid == 0) loss_acc += (sloss[0] + sloss[1]) + (sloss[2] + sloss[3]);
+    // ---- backward: deltas ----
+    tr2_gemm<4, kH3, 4, 2>(D4, sm + kTr2OffWT4, [&](int r0, int c0, float (&a)[4][2]) { tr2_store_delta<4, 2>(D3, H3, r0, c0, a); });
+    __syncthreads();
+    tr2_gemm<kH3, kH2, 8, 2>(D3, sm + kTr2OffWT3, [&](int r0, int c0, float (&a)[8][2]) { tr2_store_delta<8, 2>(D2, H2, r0, c0, a); });
+    __syncthreads();
+    tr2_gemm<kH2, kH1, 8, 4>(D2, sm + kTr2OffWT2, [&](int r0, int c0, float (&a)[8][4]) { tr2_store_delta<8, 4>(D1, H1, r0, c0, a); });
+    __syncthreads();
+    // ---- weight (and, through the rows of ones, bias) gradients, accumulated over this CTA's tiles ----
+    if (g0.layer >= 0) tr2_grad_accumulate(sm, g0, acc0);
+    if (g1.layer >= 0) tr2_grad_accumulate(sm, g1, acc1);
   }
-  // block loss (fixed order: warp shuffles, then the four warp sums)
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) loss += __shfl_down_sync(0xffffffffu, loss, o);
-  if ((tid & 31) == 0) sloss[tid >> 5] = loss;
-  __syncthreads();
   float* g = partial + static_cast<long long>(blockIdx.x) * (kNParams + 1);
-  train_layer_grad<kNFeat, kH1, kPX, kPH1>(sx, sd1, rows, g + kOffW1, g + kOffB1);
-  train_layer_grad<kH1, kH2, kPH1, kPH2>(sh1, sd2, rows, g + kOffW2, g + kOffB2);
-  train_layer_grad<kH2, kH3, kPH2, kPH3>(sh2, sd3, rows, g + kOffW3, g + kOffB3);
-  train_layer_grad<kH3, kNCls, kPH3, kPD4>(sh3, sd4, rows, g + kOffW4, g + kOffB4);
-  if (tid == 0) g[kNParams] = ((sloss[0] + sloss[1]) + (sloss[2] + sloss[3])) * inv_b;
+  tr2_grad_write(g, g0, acc0);
+  tr2_grad_write(g, g1, acc1);
+  if (tid == 0) g[kNParams] = loss_acc * inv_b;
 }
 
 // state: [0] parameters, [1] accumulated squared gradients a, [2] accumulated squared updates d (kNParams each)

@@ -100,7 +100,7 @@ struct vadb200_trainer {
   long long max_batch = 0;
   float lr = 1.0f, rho = 0.95f, eps = 1e-8f;
   float* d_state = nullptr;    // params | acc_g | acc_u   (3 x kNParams)
-  float* d_partial = nullptr;  // [ceil(max_batch / 128)][kNParams + 1]
+  float* d_partial = nullptr;  // [min(ceil(max_batch / 128), SMs)][kNParams + 1]
   float* d_loss = nullptr;
   long long steps = 0;
 };
@@ -870,7 +870,7 @@ int vadb200_trainer_create(vadb200_handle* h, int64_t max_batch, float lr, float
   if (e == cudaSuccess) e = cudaMalloc(&t->d_partial, n_part * (kNParams + 1) * sizeof(float));
   if (e == cudaSuccess) e = cudaMalloc(&t->d_loss, sizeof(float));
   if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(ffn_train_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrainSmemBytes);
+    e = cudaFuncSetAttribute(ffn_train_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrain2SmemBytes);
   if (e != cudaSuccess) {
     cudaFree(t->d_state); cudaFree(t->d_partial); cudaFree(t->d_loss);
     delete t;
@@ -925,9 +925,10 @@ int vadb200_train_on_batch(vadb200_trainer* t, const float* d_x, const uint8_t* 
   if (n > t->max_batch) return fail(VADB200_E_INVALID, "batch larger than the trainer's max_batch");
   CU(cudaSetDevice(t->h->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int n_part = static_cast<int>((n + kTrainRows - 1) / kTrainRows);
-  ffn_train_grad_kernel<<<n_part, kTrainRows, kTrainSmemBytes, st>>>(t->d_state, d_x, d_y, n, 1.0f / static_cast<float>(n),
-                                                                      t->d_partial);
+  const int n_tiles = static_cast<int>((n + kTrainRows - 1) / kTrainRows);
+  const int n_part = std::min(n_tiles, t->h->num_sms);   // persistent CTAs: one partial gradient each
+  ffn_train_grad_kernel<<<n_part, kTr2Threads, kTrain2SmemBytes, st>>>(t->d_state, d_x, d_y, n,
+                                                                         1.0f / static_cast<float>(n), t->d_partial);
   ffn_train_update_kernel<<<(kNParams + 1 + 255) / 256, 256, 0, st>>>(t->d_state, t->d_state + kNParams,
                                                                        t->d_state + 2 * kNParams, t->d_partial, n_part,
                                                                        t->lr, t->rho, t->eps, t->d_loss);
