@@ -76,6 +76,30 @@ def test_100_steps_track_the_oracle_loss():
 
 
 @pytest.mark.gpu
+def test_steps_on_batches_larger_than_the_grid_match_the_oracle():
+    """More 128-row tiles than persistent CTAs (every CTA accumulates several tiles in registers), a ragged last tile,
+    and a batch smaller than one tile: loss and updated weights after each step against the float64 restatement."""
+    import torch
+    from vad_b200 import runtime
+    from vad_b200.trainer import FFNTrainer
+    h = runtime.Handle()
+    w0 = rm.glorot_ffn(21)
+    n_big = 128 * 148 * 2 + 128 * 17 + 37                     # > 2 tiles per CTA on a 148-SM part, ragged tail
+    tr = FFNTrainer(h, weights=w0, max_batch=n_big)
+    st = rt.init_state(w0)
+    x, y = _toy_problem(n_big, 13)
+    dx, dy = torch.from_numpy(x).to(h.device), torch.from_numpy(y).to(h.device)
+    for n in (n_big, 37, 128 * 149, n_big):
+        loss = tr.train_on_batch(dx[:n].contiguous(), dy[:n].contiguous())
+        ref = rt.train_on_batch(st, x[:n], y[:n])
+        assert abs(loss - ref) <= 1e-4 * ref, (n, loss, ref)
+        got = tr.weights()
+        for k in rt.KEYS:
+            assert np.all(np.abs(got[k] - st["p"][k]) <= 1e-4 + 1e-3 * np.abs(st["p"][k])), (n, k)
+    tr.close()
+
+
+@pytest.mark.gpu
 def test_weights_round_trip_into_the_inference_path(tmp_path):
     import torch
     from vad_b200 import runtime
