@@ -1,22 +1,28 @@
 // vad_kernels.cuh -- sm_100a kernels of the fused MFCC + FFN VAD path.
 //
-// fused_kernel<MODE>: persistent CTAs (2 per SM, 256 threads) pull *segments* (runs of
+// fused_kernel<MODE, TC>: persistent CTAs (2 per SM, 256 threads) pull *segments* (runs of
 // consecutive frames of one utterance) from an atomic work counter.  Per 32-frame step:
 //   1. PCM for the step (5360 int16 = 31 hops + one frame) arrives in shared memory by one
 //      TMA bulk copy (cp.async.bulk + mbarrier), double-buffered one step ahead; overlapping
 //      frames are re-read from shared memory, never from HBM.
-//   2. FFT phase: each warp transforms 4 frames in ONE pass: a half-warp (16 threads) carries two
+//   2. FFT: each warp transforms 4 frames in ONE pass: a half-warp (16 threads) carries two
 //      frames per thread as packed register pairs, so every butterfly / twiddle / split / power
 //      operation is one FFMA2 / FADD2 / FMUL2 for both frames (sm_100a packed fp32):
 //      pruned DFT16 -> twiddle -> 16x16 transpose in shared memory (re plane, then im plane)
-//      -> DFT16 -> partner shuffle -> real-FFT split -> |X|^2 into the P tile [256 bins][32 cols].
-//   3. mel + log phase: lane = frame, warp = one of 8 balanced filter groups; weights are
-//      constant-bank FFMA operands; exact-zero -> eps; log2.
-//   4. DCT phase: lane = frame, warp = coefficient; folded DCT-II x lifter x log10(2) matrix;
-//      result goes to a 288-slot MFCC ring in shared memory (carries the +-2 frame halo
+//      -> DFT16 -> partner shuffle -> real-FFT split -> |X|^2 into the pair tile
+//      [123 bin pairs + sink row][32 cols][2 bins] through per-thread base pointers (P2Store).
+//   3. mel + log: lane = frame, warps 3-7 each own a run of consecutive filters and load every
+//      power pair once (mel2_run); weights are uniform-register FFMA2 operands; exact-zero -> eps; log2.
+//   4. DCT, one step behind: lane = frame, warps 0-3 transform two coefficient pairs per pass over
+//      the 26 log-energies (folded DCT-II x lifter x log10(2) matrix); the result is a 64-bit element
+//      of the 288-slot coefficient-pair MFCC ring in shared memory (carries the +-2 frame halo
 //      across steps, so no frame is ever transformed twice inside a segment).
-// Every 8 steps (256 frames) the block phase runs one thread per output frame: 5-frame window
-// features, Dense 39-64-32-16-3 from constant-bank operands, argmax == VOICED, 1-byte label.
+// The step has no CTA-wide bar.sync: two split-phase mbarriers ("P free", "P full", one arrival per
+// warp) order the power tile; only block steps use CTA barriers.
+// Block phase: MODE 0 / 1 flush MFCC / dataset rows (every 8 steps); MODE 2 builds the 5-frame window
+// features and runs Dense 39-64-32-16-3 -- on FP32 CUDA cores (TC = 0, every 8 steps) or as one
+// tcgen05 tile of 128 frames with TMEM accumulators (TC = 1 tf32, TC = 2 fp16 hi/lo operands; every
+// 4 steps) -- then argmax == VOICED, 1-byte label.
 //
 // Reference lines restated: mfcc.py:59-78; dataset/file_processing.py:47-70,99-101;
 // realtime_analysis/sklearn_analyser.py:46-82,103-107; learning/ffn_trainer.py:104-116.
