@@ -420,43 +420,9 @@ VADB_HD void mel_group_dispatch(int g, const float* P, float* logE) {
   }
 }
 
-// Packed mel: P2 points at this lane's column of the pair tile (row r = pair row - kP2FirstRow at P2 + r * PITCH2,
-// two floats = bins 2q, 2q+1).  One LDS.64 + one FFMA2 per bin pair; the weight pair is a uniform operand.
-template <int G, int PITCH2, int OPITCH>
-VADB_HD void mel2_group(const float* P2, float* logE) {
-  static_for<0, kMelGroupCount[G]>([&](auto J) {
-    constexpr int m = kMelGroupFilter[G][J];
-    constexpr int q0 = mel_q0(m), nq = mel_nq(m), off = mel_qoff(m);
-    f2 a0 = mk2(0.0f, 0.0f), a1 = a0, a2 = a0, a3 = a0;   // four chains: dependent-FFMA2 latency / 4
-    static_for<0, nq>([&](auto Q) {
-      constexpr int q = Q;
-      const float* pp = P2 + (q0 + q - kP2FirstRow) * PITCH2;
-      const f2 pv = mk2(pp[0], pp[1]);
-      const f2 wv = mk2(c_tab.melw2[2 * (off + q)], c_tab.melw2[2 * (off + q) + 1]);
-      if constexpr ((q & 3) == 0) a0 = vfma(pv, wv, a0);
-      else if constexpr ((q & 3) == 1) a1 = vfma(pv, wv, a1);
-      else if constexpr ((q & 3) == 2) a2 = vfma(pv, wv, a2);
-      else a3 = vfma(pv, wv, a3);
-    });
-    const f2 s = vadd(vadd(a0, a2), vadd(a1, a3));
-    logE[m * OPITCH] = log2_energy(s.x + s.y);
-  });
-}
-template <int PITCH2, int OPITCH>
-VADB_HD void mel2_group_dispatch(int g, const float* P2, float* logE) {
-  switch (g) {
-    case 0: mel2_group<0, PITCH2, OPITCH>(P2, logE); break;
-    case 1: mel2_group<1, PITCH2, OPITCH>(P2, logE); break;
-    case 2: mel2_group<2, PITCH2, OPITCH>(P2, logE); break;
-    case 3: mel2_group<3, PITCH2, OPITCH>(P2, logE); break;
-    case 4: mel2_group<4, PITCH2, OPITCH>(P2, logE); break;
-    case 5: mel2_group<5, PITCH2, OPITCH>(P2, logE); break;
-    case 6: mel2_group<6, PITCH2, OPITCH>(P2, logE); break;
-    default: mel2_group<7, PITCH2, OPITCH>(P2, logE); break;
-  }
-}
-// Load-sharing packed mel: warp g owns the run of consecutive filters kMelRunFirst[g] .. kMelRunLast[g] and walks the
-// pair rows they cover once -- every power pair is loaded a single time (LDS.64) and feeds each filter whose triangle
+// Load-sharing packed mel: P2 points at this lane's column of the pair tile (row r = pair row - kP2FirstRow at
+// P2 + r * PITCH2, two floats = bins 2q, 2q+1).  Warp g owns the run of consecutive filters kMelRunFirst[g] ..
+// kMelRunLast[g] and walks the pair rows they cover once -- every power pair is loaded a single time (LDS.64) and feeds each filter whose triangle
 // contains it (neighbouring triangles overlap by half: two FFMA2 per load in the interior).  Two accumulator chains per
 // filter; with two or three filters live per row that is four to six independent FFMA2 chains.
 template <int G, int PITCH2, int OPITCH>
