@@ -8,7 +8,7 @@
 //   a <- rho a + (1 - rho) g^2;  u = g sqrt(d + eps) / sqrt(a + eps);  theta <- theta - lr u;  d <- rho d + (1 - rho) u^2
 //
 // Two kernels per step, both deterministic (no floating-point atomics):
-//   ffn_train_grad_kernel  persistent CTAs (256 threads) walk tiles of 128 batch rows: forward, deltas and weight
+//   ffn_train_grad_kernel  persistent CTAs (512 threads) walk tiles of 128 batch rows: forward, deltas and weight
 //                           gradients as register-tiled products over transposed shared-memory tiles (below); weight
 //                           gradients stay in registers across a CTA's tiles -> one partial gradient + partial loss per CTA.
 //   ffn_train_update_kernel thread = parameter: sums the partials in CTA order, applies Adadelta in place.
@@ -27,14 +27,14 @@ constexpr int kOffW1 = 0, kOffB1 = kOffW1 + kNFeat * kH1, kOffW2 = kOffB1 + kH1,
               kOffW3 = kOffB2 + kH2, kOffB3 = kOffW3 + kH2 * kH3, kOffW4 = kOffB3 + kH3, kOffB4 = kOffW4 + kH3 * kNCls;
 static_assert(kOffB4 + kNCls == kNParams, "layout");
 // ---- gradient kernel: register-tiled, persistent --------------------------------------------------------------------
-// One CTA (256 threads) walks tiles of 128 batch rows.  Activations and deltas live in shared memory TRANSPOSED
+// One CTA (512 threads) walks tiles of 128 batch rows.  Activations and deltas live in shared memory TRANSPOSED
 // ([feature][128 rows]), so every product A^T B, D W^T and A^T D of the step is the same register-tiled loop: a thread
-// owns RM rows x CN columns (or 4 x 4 weight-gradient entries), reads its operands with 64 / 128-bit loads and does
-// 8-10 FMAs per load instead of one FMA per two loads.  Each activation buffer carries a row of ones after its
+// owns 4 rows x 1-4 columns (or 4 x 4 weight-gradient entries), reads its operands with up to 128-bit loads and does
+// 4-8 FMAs per load instead of one FMA per two loads; sixteen warps per SM cover the load latency.  Each activation buffer carries a row of ones after its
 // features, so the bias gradients fall out of the weight-gradient tiles.  Weight gradients stay in registers across
 // the CTA's tiles and are written once as this CTA's partial (summed by ffn_train_update_kernel in CTA order):
 // deterministic for a given grid, no floating-point atomics.
-constexpr int kTr2Threads = 256;
+constexpr int kTr2Threads = 512;
 constexpr int kTr2KX = 40, kTr2KH1 = 68, kTr2KH2 = 36, kTr2KH3 = 20;     // rows of X^T / H^T incl. the ones row, padded to 4
 constexpr int kTr2OffWT2 = ((kNParams + 3) / 4) * 4;                      // WT2[n][k] = W2[k][n]: [32][64]
 constexpr int kTr2OffWT3 = kTr2OffWT2 + kH2 * kH1;                        // [16][32]
@@ -56,7 +56,7 @@ static_assert(kTrainRows * 41 <= kH1 * kTrainRows, "row-major staging of an inpu
 template <int K, int N, int RM, int CN, class EPI>
 __device__ __forceinline__ void tr2_gemm(const float* __restrict__ At, const float* __restrict__ B, EPI&& epi) {
   constexpr int CG = N / CN;
-  static_assert((kTrainRows / RM) * CG == kTr2Threads && RM % 4 == 0 && (CN == 2 || CN == 4), "thread tiling");
+  static_assert((kTrainRows / RM) * CG == kTr2Threads && RM % 4 == 0 && (CN == 1 || CN == 2 || CN == 4), "thread tiling");
   const int tc = threadIdx.x % CG, tr = threadIdx.x / CG;
   float acc[RM][CN];
 #pragma unroll
@@ -76,9 +76,11 @@ __device__ __forceinline__ void tr2_gemm(const float* __restrict__ At, const flo
     if constexpr (CN == 4) {
       const float4 v = *reinterpret_cast<const float4*>(bp + k * N);
       b[0] = v.x; b[1] = v.y; b[2] = v.z; b[3] = v.w;
-    } else {
+    } else if constexpr (CN == 2) {
       const float2 v = *reinterpret_cast<const float2*>(bp + k * N);
       b[0] = v.x; b[1] = v.y;
+    } else {
+      b[0] = bp[k * N];
     }
 #pragma unroll
     for (int i = 0; i < RM; ++i)
@@ -115,8 +117,8 @@ __device__ __forceinline__ void tr2_store_delta(float* Dt, const float* Ht, int 
 }
 
 // A weight-gradient tile: 4 rows of an activation buffer (k0 ..) x 4 rows of a delta buffer (n0 ..), summed over rows.
-// 337 tiles over 256 threads: two rounds, the second 32 % full.  (4 x 2 tiles in three rounds balance better and were
-// measured 8 % slower: 50 % more shared-memory loads per FMA.)
+// 337 tiles, one per thread of the 512 (66 % of the threads busy in this stage; 4 x 2 tiles balance better and were
+// measured 8 % slower: 50 % more shared-memory loads per FMA).
 struct Tr2GradTile {
   int a_off, d_off;   // shared-memory offsets (floats) of the 4 activation rows / 4 delta rows
   int layer, k0, n0;  // where the 16 sums go; layer < 0: no tile
@@ -192,12 +194,12 @@ __global__ void __launch_bounds__(kTr2Threads, 1) ffn_train_grad_kernel(const fl
     for (int k = kH3; k < kTr2KH3; ++k) sm[kTr2OffH3 + k * kTrainRows + i] = k == kH3 ? 1.0f : 0.0f;
     sm[kTr2OffD4 + 3 * kTrainRows + i] = 0.0f;
   }
-  const Tr2GradTile g0 = tr2_grad_tile(tid), g1 = tr2_grad_tile(tid + kTr2Threads);
-  float acc0[4][4], acc1[4][4];
+  const Tr2GradTile g0 = tr2_grad_tile(tid);   // 337 tiles: threads 337 .. 511 own none
+  float acc0[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc0[i][j] = acc1[i][j] = 0.0f;
+    for (int j = 0; j < 4; ++j) acc0[i][j] = 0.0f;
   float loss_acc = 0.0f;   // thread 0 only: tile losses in tile order
   float* X = sm + kTr2OffX;
   float* H1 = sm + kTr2OffH1;
@@ -226,11 +228,11 @@ __global__ void __launch_bounds__(kTr2Threads, 1) ffn_train_grad_kernel(const fl
     }
     __syncthreads();
     // ---- forward (learning/ffn_trainer.py:106-116) ----
-    tr2_gemm<kNFeat, kH1, 8, 4>(X, w + kOffW1, [&](int r0, int c0, float (&a)[8][4]) { tr2_store_relu<8, 4>(H1, w + kOffB1, r0, c0, a); });
+    tr2_gemm<kNFeat, kH1, 4, 4>(X, w + kOffW1, [&](int r0, int c0, float (&a)[4][4]) { tr2_store_relu<4, 4>(H1, w + kOffB1, r0, c0, a); });
     __syncthreads();
-    tr2_gemm<kH1, kH2, 8, 2>(H1, w + kOffW2, [&](int r0, int c0, float (&a)[8][2]) { tr2_store_relu<8, 2>(H2, w + kOffB2, r0, c0, a); });
+    tr2_gemm<kH1, kH2, 4, 2>(H1, w + kOffW2, [&](int r0, int c0, float (&a)[4][2]) { tr2_store_relu<4, 2>(H2, w + kOffB2, r0, c0, a); });
     __syncthreads();
-    tr2_gemm<kH2, kH3, 4, 2>(H2, w + kOffW3, [&](int r0, int c0, float (&a)[4][2]) { tr2_store_relu<4, 2>(H3, w + kOffB3, r0, c0, a); });
+    tr2_gemm<kH2, kH3, 4, 1>(H2, w + kOffW3, [&](int r0, int c0, float (&a)[4][1]) { tr2_store_relu<4, 1>(H3, w + kOffB3, r0, c0, a); });
     __syncthreads();
     // ---- layer 4, softmax, categorical cross-entropy, dlogits: thread = row ----
     float loss = 0.0f;
@@ -262,19 +264,17 @@ __global__ void __launch_bounds__(kTr2Threads, 1) ffn_train_grad_kernel(const fl
     __syncthreads();
     if (tid == 0) loss_acc += (sloss[0] + sloss[1]) + (sloss[2] + sloss[3]);
     // ---- backward: deltas ----
-    tr2_gemm<4, kH3, 4, 2>(D4, sm + kTr2OffWT4, [&](int r0, int c0, float (&a)[4][2]) { tr2_store_delta<4, 2>(D3, H3, r0, c0, a); });
+    tr2_gemm<4, kH3, 4, 1>(D4, sm + kTr2OffWT4, [&](int r0, int c0, float (&a)[4][1]) { tr2_store_delta<4, 1>(D3, H3, r0, c0, a); });
     __syncthreads();
-    tr2_gemm<kH3, kH2, 8, 2>(D3, sm + kTr2OffWT3, [&](int r0, int c0, float (&a)[8][2]) { tr2_store_delta<8, 2>(D2, H2, r0, c0, a); });
+    tr2_gemm<kH3, kH2, 4, 2>(D3, sm + kTr2OffWT3, [&](int r0, int c0, float (&a)[4][2]) { tr2_store_delta<4, 2>(D2, H2, r0, c0, a); });
     __syncthreads();
-    tr2_gemm<kH2, kH1, 8, 4>(D2, sm + kTr2OffWT2, [&](int r0, int c0, float (&a)[8][4]) { tr2_store_delta<8, 4>(D1, H1, r0, c0, a); });
+    tr2_gemm<kH2, kH1, 4, 4>(D2, sm + kTr2OffWT2, [&](int r0, int c0, float (&a)[4][4]) { tr2_store_delta<4, 4>(D1, H1, r0, c0, a); });
     __syncthreads();
     // ---- weight (and, through the rows of ones, bias) gradients, accumulated over this CTA's tiles ----
     if (g0.layer >= 0) tr2_grad_accumulate(sm, g0, acc0);
-    if (g1.layer >= 0) tr2_grad_accumulate(sm, g1, acc1);
   }
   float* g = partial + static_cast<long long>(blockIdx.x) * (kNParams + 1);
   tr2_grad_write(g, g0, acc0);
-  tr2_grad_write(g, g1, acc1);
   if (tid == 0) g[kNParams] = loss_acc * inv_b;
 }
 
